@@ -1,0 +1,155 @@
+/*
+ * danet.h -- C ABI of libdanet_sm100.so: the B200 (sm_100a) kernels behind the
+ * Encoder / Estimator / Separator plugin surface of khaotik/DaNet-Tensorflow.
+ *
+ * Conventions:
+ *   - every entry point returns int: 0 = DANET_OK, negative = error; never throws,
+ *     never allocates or frees device memory; the caller owns every buffer,
+ *     including workspaces whose sizes come from the *_workspace_bytes queries;
+ *   - all pointers are DEVICE pointers unless the name says `host_`;
+ *   - kernels are asynchronous on the passed stream (a cudaStream_t cast to void*);
+ *   - float tensors are contiguous fp32, complex tensors interleaved (re,im) fp32,
+ *     index tensors int32; shapes follow the reference ([B,C,T,F], [B,T,F,E], ...);
+ *   - F = 129 bins (FFT_SIZE 256, FFT_STRIDE 64) is the only front-end geometry.
+ *
+ * Each declaration cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef DANET_H_
+#define DANET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DANET_OK          0
+#define DANET_E_SHAPE    -1   /* unsupported / inconsistent sizes            */
+#define DANET_E_ALIGN    -2   /* pointer not aligned as required             */
+#define DANET_E_ARCH     -3   /* device is not sm_100                        */
+#define DANET_E_CUDA     -4   /* a CUDA runtime call failed (see last error) */
+#define DANET_E_ARG      -5   /* null pointer / bad enum                     */
+#define DANET_E_WORKSPACE -6  /* workspace too small                         */
+
+#define DANET_FFT_SIZE   256
+#define DANET_FFT_STRIDE 64
+#define DANET_FEATURE    129
+
+/* library identity; danet_last_error_string() is thread-local, never NULL */
+int         danet_version(void);
+const char* danet_last_error_string(void);
+/* 0 if the current device is compute capability 10.x, DANET_E_ARCH otherwise */
+int         danet_check_device(void);
+
+/* ---- K1  STFT front end -------------------------------------------------
+ * replaces scipy.signal.stft as called at app/utils.py:117-122,
+ * app/datasets/TIMIT/process.py:93-97 (window default.json:7): zero-pad 128 both
+ * sides + tail to a hop multiple, frames of 256 @ hop 64, sqrt-hann, rFFT, 1/sum(w).
+ * wav [n_sig, n_samples] -> spec [n_sig, T, 129] complex, T = ceil(n/64)+1.
+ * logmag (nullable) [n_sig, T, 129] = log1p(|spec|)   (main.py:239-240).
+ * n_samples < 256 -> DANET_E_SHAPE (scipy raises ValueError there). */
+int danet_stft_num_frames(int n_samples);
+int danet_stft_fwd(const float* wav, int n_sig, int n_samples,
+                   float* spec_c64, float* logmag, void* stream);
+
+/* ---- mixture features ---------------------------------------------------
+ * replaces main.py:233-240: mix = sum_c src; src_pwr = |src|; mix_pwr = |mix|;
+ * logmag = log1p(mix_pwr).  src [B,C,T,F] complex.  Any output may be NULL. */
+int danet_mix_features_fwd(const float* src_c64, int B, int C, int TF,
+                           float* mix_c64, float* src_pwr, float* mix_pwr,
+                           float* logmag, void* stream);
+
+/* ---- per-utterance mean centring -----------------------------------------
+ * replaces app/modules.py:209-210 and :244-245 (x - mean over axes (1,2)).
+ * x [B, n_per] -> y [B, n_per] (y may alias x).  workspace: B*64 floats. */
+size_t danet_center_workspace_bytes(int B);
+int danet_center_fwd(const float* x, int B, long long n_per, float* y,
+                     float* workspace, void* stream);
+
+/* ---- dense layers (input projections of the LSTM, output projection) ------
+ * replaces app/ops.py:37-90 (lyr_linear, last-axis branch :72-89).
+ * C[M,N] = A[M,K] (row stride lda) * W[K,N] (row stride ldw) (+ bias[N]).
+ * If time_major_T > 0 the logical row r = b*T + t of A is written to output row
+ * t*(M/T) + b (the [T,B,N] layout the recurrent kernel consumes).
+ * backend: 0 = exact fp32 SIMT, 1 = tcgen05 bf16x3 (fp32-grade split precision). */
+int danet_linear_fwd(const float* A, long long lda, const float* W, long long ldw,
+                     const float* bias, float* C, int M, int N, int K,
+                     int time_major_T, int backend, void* stream);
+
+/* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------
+ * replaces Model.lyr_lstm (main.py:76-132: tf.scan from zero state) over
+ * ops.lyr_lstm_flat (app/ops.py:139-147: gates [cand|i|f|o], candidate WITHOUT tanh,
+ * c' = i*g + f*c, h' = o*tanh(c')) and _lyr_bilstm (app/modules.py:120-137).
+ *   pre   [n_dir][T][B][4H]  x_t*Wx + bias for every step (danet_linear_fwd output);
+ *         direction 1 is indexed by ORIGINAL time (it walks t = T-1 .. 0)
+ *   Wh    n_dir pointers to the recurrent rows W[I:I+H, 0:4H] (row stride ldw)
+ *   out   [B][T][n_dir*H]  hidden sequence, fwd in [0,H), bwd in [H,2H) (un-reversed)
+ *   cell_seq (nullable) [n_dir][T][B][H] cell states kept for the backward pass
+ * backend: 0 = fp32 SIMT cooperative kernel, 1 = tcgen05 cluster kernel. */
+size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H);
+int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
+                       float* out, float* cell_seq, int n_dir, int T, int B, int H,
+                       void* workspace, size_t workspace_bytes, int backend, void* stream);
+
+/* ---- K3  attractor estimation ---------------------------------------------
+ * truth family replaces app/modules.py:390-412 (mode 0: plain, denominator n+1),
+ * :425-450 (mode 1: weight = mix_pwr > 5, + EPS), :462-487 (mode 2: weight =
+ * mix_pwr, + EPS).  class = first argmax_c src_pwr[b,:,t,f].
+ *   embed [B,TF,E], src_pwr [B,C,TF], mix_pwr [B,TF] -> attractors [B,C,E] */
+size_t danet_attractor_workspace_bytes(int B, int n_acc_rows, int E);
+int danet_attractor_truth_fwd(const float* embed, const float* src_pwr,
+                              const float* mix_pwr, float* attractors,
+                              int B, int C, int TF, int E, int mode,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* anchor estimator replaces app/modules.py:501-545 + app/ops.py:273-292:
+ * P = C(n_anchor, C) subsets in itertools.combinations order; eq.6 softmax over the
+ * subset's anchors, eq.7 weighted means, eq.8 max over the full CxC Gram (diagonal
+ * included), eq.9 argmin.  Outputs: attractors [B,C,E]; optional attractor_sets
+ * [B,P,C,E], similarities [B,P], choice [B] int32. */
+int danet_anchor_num_subsets(int n_anchor, int C);
+int danet_attractor_anchor_fwd(const float* embed, const float* anchors,
+                               float* attractors, float* attractor_sets,
+                               float* similarities, int* choice,
+                               int B, int C, int TF, int E, int n_anchor,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* k-means estimator: NEW plugin without a reference twin (README.md:216-217 lists it
+ * as unimplemented).  Lloyd iterations on embed[b] from the given initial centroids
+ * (in/out [B,C,E]); an empty cluster keeps its previous centroid. */
+int danet_attractor_kmeans_fwd(const float* embed, float* centroids,
+                               int B, int C, int TF, int E, int n_iter,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4  mask x mixture (+ iSTFT) -------------------------------------------
+ * replaces DotSeparatorSoftmax/Sigmoid (app/modules.py:577-603 / :548-574) and the
+ * re-phasing at main.py:281-284 (complex(cos(phi)*p, sin(phi)*p) == mask * mix).
+ *   embed [B,TF,E], attractors [B,C,E], mix [B,TF] complex ->
+ *   sep_pwr (nullable) [B,C,TF]; sep_c64 (nullable) [B,C,TF] complex;
+ *   masks (nullable) [B,TF,C].   kind: 0 = softmax over C, 1 = sigmoid. */
+int danet_mask_cmul_fwd(const float* embed, const float* attractors,
+                        const float* mix_c64, float* sep_pwr, float* sep_c64,
+                        float* masks, int B, int C, int TF, int E, int kind,
+                        void* stream);
+/* replaces utils.istft (app/utils.py:53-75) incl. its quirks: frames 0..T-5 only,
+ * overlap-add of irfft(X[n])*w, division by sum(w^2) where non-zero, length 64*T.
+ * spec [n_sig,T,129] complex -> wav [n_sig, 64*T] fp32. */
+int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* stream);
+/* ---- K5  PIT-MSE + SNR ---------------------------------------------------------
+ * replaces ops.pit_mse_loss (app/ops.py:374-431), the permutation gather at
+ * main.py:293-306 and ops.batch_snr (app/ops.py:191-222).
+ *   x, y [B,C,TF] complex (is_complex=1) or real;
+ *   cross [B,C,C] mean |x_i - y_j|^2; perm_losses [B,C!] (itertools.permutations
+ *   order); perm_idx [B] int32 first argmin; loss[1] = mean_b min; snr [B] (dB of
+ *   mean|x|^2 over mean|x - y_aligned|^2, EPS 1e-7).  Outputs may be NULL except
+ *   cross.  workspace: danet_pit_workspace_bytes. */
+size_t danet_pit_workspace_bytes(int B, int C);
+int danet_pit_mse_fwd(const float* x, const float* y, int B, int C, int TF,
+                      int is_complex, float* cross, float* perm_losses, int* perm_idx,
+                      float* loss, float* snr, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DANET_H_ */

@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""
+bench.py -- mixtures/sec of the DANet separation hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], inference form): a batch of 32 synthetic 2-speaker mixtures,
+4 s @ 8 kHz, FFT 256 / hop 64 (T = 501 frames), BiLSTM encoder 4 x (300+300), EMBED 20, anchor
+estimator (6 anchors), softmax separator:  wav -> STFT -> log-magnitude -> BiLSTM -> anchor
+attractors -> mask x complex mixture -> iSTFT -> 2 separated wavs per mixture.  One step = one
+pass over one batch.  Per-GPU work is fixed (weak scaling); utterances shard across ranks with no
+data-path collective.
+
+  value  : device-resident inputs, CUDA-event time of K steps (max over ranks)
+  e2e    : the public call Model.separate_host(): pinned host wavs -> H2D -> ... -> D2H wavs
+  roofline: the dominant kernel (the persistent BiLSTM recurrence), timed live with CUDA events
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, fp32 torch-CPU,
+           all host threads) on a bounded sample of the same workload.  TensorFlow 1.x cannot be
+           installed in this image, so the restatement stands in for the TF1 reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = 'mixtures/sec (2-spk, 4s@8kHz, FFT256)'
+N_SAMPLES = 32000
+N_SPK = 2
+EMBED = 20
+HDIM = 300
+N_LAYERS = 4
+
+
+def synth_mixtures(batch, n_samples, seed):
+    """per source white noise through a one-pole low-pass (a = 0.9) x a 4 Hz
+    raised-cosine envelope with random phase, RMS 1000 (int16 scale); mixture = sum of sources."""
+    rs = np.random.RandomState(seed)
+    x = rs.standard_normal((batch, N_SPK, n_samples)).astype(np.float64)
+    y = np.empty_like(x)
+    acc = np.zeros((batch, N_SPK))
+    for i in range(n_samples):          # one-pole IIR; vectorised over (batch, source)
+        acc = 0.9 * acc + x[..., i]
+        y[..., i] = acc
+    t = np.arange(n_samples) / 8000.
+    ph = rs.uniform(0, 2 * np.pi, (batch, N_SPK, 1))
+    y *= 0.5 - 0.5 * np.cos(2 * np.pi * 4. * t + ph)
+    y *= 1000. / np.sqrt((y ** 2).mean(-1, keepdims=True))
+    return y.sum(1).astype(np.float32)
+
+
+def reference_params(seed=1337):
+    from oracle import danet_oracle as O
+    return O.reference_init(seed, encoder='bilstm-orig', embed=EMBED, estimators=('infer_estimator',),
+                            dtype=torch.float32)
+
+
+def cpu_reference_rate(wav, threads, repeats=1):
+    """mixtures/sec of the CPU restatement (oracle) on `wav` [b, N]"""
+    from oracle import danet_oracle as O
+    torch.set_num_threads(threads)
+    P = reference_params()
+    O.separate_waveforms(wav[:1, :2048], P, dtype=torch.float32)      # warm the thread pool
+    best = float('inf')
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.separate_waveforms(wav, P, dtype=torch.float32)
+        best = min(best, time.perf_counter() - t0)
+    return wav.shape[0] / best, best
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0., set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    b = args.ref_batch
+    wav = synth_mixtures(b, N_SAMPLES, 1337)
+    times = []
+    P = reference_params()
+    from oracle import danet_oracle as O
+    torch.set_num_threads(threads)
+    O.separate_waveforms(wav[:1, :2048], P, dtype=torch.float32)
+    steps = max(1, min(args.steps, args.ref_steps))
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.separate_waveforms(wav, P, dtype=torch.float32)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = b / (ms / 1e3)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'mixtures/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(b, 'cpu'),
+        'cpu_baseline': {'value': val, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d mixtures of 4 s per step, %d steps; torch-CPU fp32 restatement of the TF1 '
+                                   'graph (TensorFlow 1.x is not installable here)' % (b, steps)},
+        'e2e': {'value': val, 'unit': 'mixtures/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, where):
+    return {'workload': 'cfg2-infer: wav->STFT->logmag->BiLSTM 4x(300+300)->anchor(6)->softmax mask x mix->iSTFT',
+            'batch_per_gpu': batch, 'n_speakers': N_SPK, 'samples': N_SAMPLES, 'frames': 501, 'fft': 256,
+            'hop': 64, 'embed': EMBED, 'estimator': 'anchor', 'separator': 'dot-softmax-orig',
+            'parallelism': 'utterance-sharded, no collective', 'l2': 'flushed between timed steps', 'where': where}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='mixtures per GPU per step')
+    ap.add_argument('--backend', type=int, default=None, help='0 = fp32 SIMT, 1 = tcgen05')
+    ap.add_argument('--ref-batch', type=int, default=32)
+    ap.add_argument('--ref-steps', type=int, default=5)
+    ap.add_argument('--cpu-baseline-mixtures', type=int, default=32)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import danet_tensorflow_b200 as D
+    K = D.kernels
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback for the product path)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    if args.backend is not None:
+        K.DEFAULT_BACKEND = args.backend
+    D.build.build()
+    D._lib.check(D._lib.load().danet_check_device(), 'check_device')
+
+    hp = D.hparams
+    hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=args.batch, EMBED_SIZE=EMBED, MAX_N_SIGNAL=N_SPK))
+    hp.digest()
+    model = D.Model('bench', dev, seed=1337).build()
+    B = args.batch
+    wav_np = synth_mixtures(B, N_SAMPLES, 1337 + rank)
+    wav_host = torch.from_numpy(wav_np).pin_memory()
+    wav_dev = wav_host.to(dev)
+    T = K.num_frames(N_SAMPLES)
+    out_host = torch.empty((B, N_SPK, 64 * T), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    # instrument the dominant kernel (recurrent LSTM) with events on the launching stream
+    lstm_events = []
+    raw_lstm = K.lstm_seq
+
+    def timed_lstm(*a, **kw):
+        if not timed_lstm.on:
+            return raw_lstm(*a, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = raw_lstm(*a, **kw)
+        e1.record()
+        lstm_events.append((e0, e1))
+        return r
+    timed_lstm.on = False
+    K.lstm_seq = timed_lstm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, steps):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        model.separate(wav_dev)
+        model.separate_host(wav_host, out_host)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    K.launches = 0
+    timed_lstm.on = True
+    ms_dev = timed_loop(lambda: model.separate(wav_dev), args.steps)
+    timed_lstm.on = False
+    launches = K.launches
+    lstm_ms = [a.elapsed_time(b) for a, b in lstm_events]
+    ms_e2e = timed_loop(lambda: model.separate_host(wav_host, out_host), args.steps)
+    clocks = sampler.stop()
+
+    total = B * world
+    value = total * args.steps / (ms_dev / 1e3)
+    e2e = total * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    # algorithmic flops of one recurrent launch (one BiLSTM layer): h_{t-1} * Wh for both directions
+    flops = 2. * 2 * B * HDIM * 4 * HDIM * T
+    lstm_avg_ms = float(np.mean(lstm_ms)) if lstm_ms else None
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.)
+    achieved = flops / (lstm_avg_ms * 1e-3) / 1e12 if lstm_avg_ms else None
+    roofline = {'bound': 'tensor', 'kernel': 'lstm_seq (BiLSTM recurrence, one launch per layer)',
+                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': achieved / peak_tf if achieved else None, 'traffic': None,
+                'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)'
+                if peaks else 'fallback',
+                'ms_per_launch': lstm_avg_ms, 'launches_per_step': N_LAYERS,
+                'share_of_step': (sum(lstm_ms) / ms_dev) if lstm_ms else None,
+                'note': 'algorithmic fp32 flops 2*n_dir*B*H*4H*T; the kernel is bound by the latency of T '
+                        'dependent steps, not by tensor throughput'}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        nb = args.cpu_baseline_mixtures
+        rate, secs = cpu_reference_rate(wav_np[:nb], threads, repeats=3)
+        cpu_baseline = {'value': rate, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
+                        'sample': '%d of the %d mixtures of one step, best of 3 (%.1f s each); torch-CPU fp32 restatement of '
+                                  'the TF1 graph' % (nb, B, secs)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'mixtures/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (bf16x3 split operands on tcgen05, fp32 accumulate)'
+        if K.DEFAULT_BACKEND == 1 else 'f32',
+        'data': 'synthetic', 'config': workload_config(B, 'cuda'),
+        'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
+                'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
+        'backend': K.DEFAULT_BACKEND,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

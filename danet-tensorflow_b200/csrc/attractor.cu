@@ -1,0 +1,384 @@
+// K3: attractor estimation -- one streaming pass over the embedding per call.
+//   truth family  app/modules.py:390-412 / 425-450 / 462-487
+//   anchor        app/modules.py:501-545 + app/ops.py:273-292
+//   k-means       new plugin (README.md:216-217 lists it as unimplemented)
+// All three are "per-bin row weights, then a weighted sum of embedding vectors":
+//   acc[r][e] += Wt[tf][r] * V[tf][e],  den[r] += Wt[tf][r]
+// with R rows = C (truth, k-means: one-hot class x weight) or P*C (anchor: softmax over
+// every anchor subset).  A block stages a tile of V in shared memory with coalesced
+// float4 loads, phase 1 computes Wt for the tile (one thread per bin), phase 2 is a small
+// register-tiled product.  Partials go to the workspace; a finalize kernel reduces them in
+// a fixed order (deterministic, no atomics) and applies the estimator's epilogue.
+#include "common.cuh"
+
+namespace danet {
+
+constexpr int kTile = 128;        // bins per tile
+constexpr int kAttMaxC = 4;
+constexpr int kAttMaxE = 128;
+constexpr int kAttMaxRows = 80;   // C(6,3)*3 = 60
+constexpr int kMaxAnchor = 8;
+constexpr int kParts = 32;        // blocks per utterance
+constexpr int kMaxAccPerThread = 4;
+
+enum { MODE_TRUTH = 0, MODE_ANCHOR = 1, MODE_KMEANS = 2 };
+
+struct AttParams {
+  const float* embed;     // [B][TF][E]
+  const float* src_pwr;   // truth: [B][C][TF]
+  const float* mix_pwr;   // truth modes 1,2: [B][TF]
+  const float* aux;       // anchor: anchors [A][E]; kmeans: centroids [B][C][E]
+  float* part;            // [B][kParts][R][nQ*4]
+  long long TF;
+  int C, E, R, nQ, ldv, n_anchor, n_sub, truth_mode;
+  int subsets[20 * kAttMaxC];   // anchor index table [P][C]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+attractor_partial_kernel(const AttParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int E = p.E, C = p.C, R = p.R, nQ = p.nQ, ldv = p.ldv;
+  float* sV = smem;                                  // [kTile][ldv]: E values, then (1,0,0,0)
+  float* sW = sV + kTile * ldv;                      // [kTile][R]
+  float* sAux = sW + kTile * R;                      // anchors / centroids
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x;
+  const long long TF = p.TF;
+  const float* Vb = p.embed + (size_t)b * TF * E;
+
+  const int n_aux = MODE == MODE_ANCHOR ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
+  for (int i = tid; i < n_aux; i += 256)
+    sAux[i] = MODE == MODE_KMEANS ? p.aux[(size_t)b * C * E + i] : p.aux[i];
+  for (int i = tid; i < kTile; i += 256) {   // constant "ones" quad feeding the denominators
+    float* q = sV + i * ldv + E;
+    q[0] = 1.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f;
+  }
+
+  // phase-2 mapping: output quads (r, q) split over G bin-interleaved groups
+  const int n_out = R * nQ;
+  const int G = n_out >= 256 ? 1 : 256 / n_out;
+  float4 acc[kMaxAccPerThread];
+#pragma unroll
+  for (int i = 0; i < kMaxAccPerThread; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const long long n_tiles = (TF + kTile - 1) / kTile;
+  const long long tiles_per = (n_tiles + kParts - 1) / kParts;
+  const long long t_lo = part * tiles_per;
+  const long long t_hi = t_lo + tiles_per < n_tiles ? t_lo + tiles_per : n_tiles;
+  const int eq = E / 4;
+  for (long long tile = t_lo; tile < t_hi; ++tile) {
+    const long long tf0 = tile * kTile;
+    const int n_here = (int)(TF - tf0 < kTile ? TF - tf0 : kTile);
+    __syncthreads();   // previous tile fully consumed (also orders the prologue stores)
+    {   // stage V tile: contiguous float4 stream
+      const float4* src = reinterpret_cast<const float4*>(Vb + (size_t)tf0 * E);
+      for (int i = tid; i < n_here * eq; i += 256) {
+        const float4 v = __ldg(src + i);
+        *reinterpret_cast<float4*>(sV + (i / eq) * ldv + 4 * (i % eq)) = v;
+      }
+    }
+    __syncthreads();
+    if (tid < kTile) {   // phase 1: row weights of bin tf0 + tid
+      float* w = sW + tid * R;
+      if (tid >= n_here) {
+        for (int r = 0; r < R; ++r) w[r] = 0.f;
+      } else if (MODE == MODE_TRUTH) {
+        const long long tf = tf0 + tid;
+        const float* sp = p.src_pwr + (size_t)b * C * TF + tf;
+        int k = 0;
+        float best = __ldg(sp);
+        for (int c = 1; c < C; ++c) {          // first maximum on ties (modules.py:396)
+          const float v = __ldg(sp + (size_t)c * TF);
+          if (v > best) { best = v; k = c; }
+        }
+        float wt = 1.f;
+        if (p.truth_mode == 1) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf) > 5.f ? 1.f : 0.f;
+        if (p.truth_mode == 2) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf);
+        for (int c = 0; c < C; ++c) w[c] = c == k ? wt : 0.f;
+      } else if (MODE == MODE_ANCHOR) {
+        float logit[kMaxAnchor];
+#pragma unroll
+        for (int a = 0; a < kMaxAnchor; ++a) logit[a] = 0.f;
+        const float* v = sV + tid * ldv;
+        for (int e = 0; e < E; e += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(v + e);
+#pragma unroll
+          for (int a = 0; a < kMaxAnchor; ++a)
+            if (a < p.n_anchor) {
+              const float* an = sAux + a * E + e;
+              logit[a] = fmaf(x.x, an[0], logit[a]);
+              logit[a] = fmaf(x.y, an[1], logit[a]);
+              logit[a] = fmaf(x.z, an[2], logit[a]);
+              logit[a] = fmaf(x.w, an[3], logit[a]);
+            }
+        }
+        for (int s = 0; s < p.n_sub; ++s) {     // eq.6: softmax over the subset's anchors
+          float l[kAttMaxC];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < kAttMaxC; ++c)
+            if (c < C) {
+              const int a = p.subsets[s * kAttMaxC + c];
+              float lv = logit[0];
+#pragma unroll
+              for (int q = 1; q < kMaxAnchor; ++q) lv = a == q ? logit[q] : lv;
+              l[c] = lv;
+              mx = fmaxf(mx, lv);
+            }
+          float den = 0.f;
+#pragma unroll
+          for (int c = 0; c < kAttMaxC; ++c)
+            if (c < C) { l[c] = expf(l[c] - mx); den += l[c]; }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int c = 0; c < kAttMaxC; ++c)
+            if (c < C) w[s * C + c] = l[c] * inv;
+        }
+      } else {   // k-means: nearest centroid, first minimum on ties
+        const float* v = sV + tid * ldv;
+        int k = 0;
+        float best = INFINITY;
+        for (int c = 0; c < C; ++c) {
+          float d = 0.f;
+          for (int e = 0; e < E; ++e) {
+            const float t = v[e] - sAux[c * E + e];
+            d = fmaf(t, t, d);
+          }
+          if (d < best) { best = d; k = c; }
+        }
+        for (int c = 0; c < C; ++c) w[c] = c == k ? 1.f : 0.f;
+      }
+    }
+    __syncthreads();
+    // phase 2: acc[r][q] += Wt[tf][r] * V[tf][4q..4q+3]
+#pragma unroll
+    for (int i = 0; i < kMaxAccPerThread; ++i) {
+      const int o = tid + i * 256;
+      if (o < G * n_out) {
+        const int g = o / n_out, rq = o % n_out, r = rq / nQ, q = rq % nQ;
+        float4 a = acc[i];
+        for (int tfl = g; tfl < n_here; tfl += G) {
+          const float wv = sW[tfl * R + r];
+          const float4 x = *reinterpret_cast<const float4*>(sV + tfl * ldv + 4 * q);
+          a.x = fmaf(wv, x.x, a.x); a.y = fmaf(wv, x.y, a.y);
+          a.z = fmaf(wv, x.z, a.z); a.w = fmaf(wv, x.w, a.w);
+        }
+        acc[i] = a;
+      }
+    }
+  }
+  // reduce the G groups through shared memory (reuse sV), fixed order
+  __syncthreads();
+  float4* red = reinterpret_cast<float4*>(smem);
+#pragma unroll
+  for (int i = 0; i < kMaxAccPerThread; ++i) {
+    const int o = tid + i * 256;
+    if (o < G * n_out) red[o] = acc[i];
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(p.part) + ((size_t)b * kParts + part) * n_out;
+  for (int rq = tid; rq < n_out; rq += 256) {
+    float4 s = red[rq];
+    for (int g = 1; g < G; ++g) {
+      const float4 t = red[g * n_out + rq];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    dst[rq] = s;
+  }
+}
+
+// one block per utterance: sum the partials, then the estimator epilogue
+template <int MODE>
+__global__ void __launch_bounds__(256)
+attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, int nQ, int n_sub,
+                          float denom_add, float* __restrict__ attractors,
+                          float* __restrict__ attractor_sets, float* __restrict__ sims,
+                          int* __restrict__ choice) {
+  __shared__ float s_sum[kAttMaxRows * (kAttMaxE + 4)];
+  __shared__ float s_sim[32];
+  __shared__ int s_choice;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ld = nQ * 4, n = R * ld;
+  for (int i = tid; i < n; i += 256) {
+    float s = 0.f;
+    for (int pt = 0; pt < kParts; ++pt) s += part[((size_t)b * kParts + pt) * n + i];
+    s_sum[i] = s;
+  }
+  __syncthreads();
+  if (MODE == MODE_TRUTH) {
+    for (int i = tid; i < C * E; i += 256) {
+      const int c = i / E, e = i % E;
+      attractors[(size_t)b * C * E + i] = s_sum[c * ld + e] / (s_sum[c * ld + E] + denom_add);
+    }
+  } else if (MODE == MODE_KMEANS) {
+    for (int i = tid; i < C * E; i += 256) {   // empty cluster keeps its previous centroid
+      const int c = i / E, e = i % E;
+      const float cnt = s_sum[c * ld + E];
+      if (cnt > 0.f) attractors[(size_t)b * C * E + i] = s_sum[c * ld + e] / cnt;
+    }
+  } else {
+    for (int i = tid; i < R * E; i += 256) {   // eq.7
+      const int r = i / E, e = i % E;
+      const float v = s_sum[r * ld + e] / s_sum[r * ld + E];
+      s_sum[r * ld + e] = v;                   // each element owned by one thread
+      if (attractor_sets) attractor_sets[(size_t)b * R * E + i] = v;
+    }
+    __syncthreads();
+    if (tid < n_sub) {                         // eq.8: max over the full C x C Gram (diagonal included)
+      float mx = -INFINITY;
+      for (int c1 = 0; c1 < C; ++c1)
+        for (int c2 = 0; c2 < C; ++c2) {
+          float d = 0.f;
+          for (int e = 0; e < E; ++e)
+            d = fmaf(s_sum[(tid * C + c1) * ld + e], s_sum[(tid * C + c2) * ld + e], d);
+          mx = fmaxf(mx, d);
+        }
+      s_sim[tid] = mx;
+      if (sims) sims[(size_t)b * n_sub + tid] = mx;
+    }
+    __syncthreads();
+    if (tid == 0) {                            // eq.9: first argmin
+      int best = 0;
+      for (int s = 1; s < n_sub; ++s)
+        if (s_sim[s] < s_sim[best]) best = s;
+      s_choice = best;
+      if (choice) choice[b] = best;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * E; i += 256) {
+      const int c = i / E, e = i % E;
+      attractors[(size_t)b * C * E + i] = s_sum[(s_choice * C + c) * ld + e];
+    }
+  }
+}
+
+static int n_choose_k(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  long long r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return (int)r;
+}
+
+static int quad_stride(int E) { return ((E / 4 + 1) | 1) * 4; }   // odd quad count: conflict-free float4 rows
+
+static size_t att_smem_bytes(int E, int R, int n_aux) {
+  size_t tile = (size_t)kTile * quad_stride(E) + (size_t)kTile * R + n_aux;
+  size_t red = (size_t)256 * kMaxAccPerThread * 4;
+  return (tile > red ? tile : red) * sizeof(float);
+}
+
+template <int MODE>
+static int launch_partial(AttParams& p, int B, int n_aux, cudaStream_t st) {
+  const size_t smem = att_smem_bytes(p.E, p.R, n_aux);
+  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "attractor: %zu B of shared memory needed", smem);
+  DANET_CUDA(cudaFuncSetAttribute(attractor_partial_kernel<MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attractor_partial_kernel<MODE><<<dim3(kParts, B), 256, smem, st>>>(p);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+static int check_common(const char* who, const float* embed, int B, int C, int TF, int E, int R,
+                        void* ws, size_t ws_bytes) {
+  DANET_REQUIRE(embed && ws, DANET_E_ARG, "%s: null pointer", who);
+  DANET_REQUIRE(B >= 0 && B <= 65535 && C >= 1 && C <= kAttMaxC && TF >= 1 && E >= 4 && E % 4 == 0 &&
+                    E <= kAttMaxE && R <= kAttMaxRows,
+                DANET_E_SHAPE, "%s: B %d C %d (<=%d) TF %d E %d (multiple of 4, <=%d) rows %d", who, B, C,
+                kAttMaxC, TF, E, kAttMaxE, R);
+  DANET_REQUIRE((size_t)R * (E / 4 + 1) <= 256 * kMaxAccPerThread, DANET_E_SHAPE,
+                "%s: %d rows x E %d exceeds the accumulator budget", who, R, E);
+  DANET_REQUIRE(aligned16(embed), DANET_E_ALIGN, "%s: embed must be 16-byte aligned", who);
+  DANET_REQUIRE(ws_bytes >= danet_attractor_workspace_bytes(B, R, E), DANET_E_WORKSPACE,
+                "%s: workspace %zu < %zu", who, ws_bytes, danet_attractor_workspace_bytes(B, R, E));
+  DANET_REQUIRE(aligned16(ws), DANET_E_ALIGN, "%s: workspace must be 16-byte aligned", who);
+  return DANET_OK;
+}
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" size_t danet_attractor_workspace_bytes(int B, int n_acc_rows, int E) {
+  if (B < 1 || n_acc_rows < 1 || E < 4) return 256;
+  return (size_t)B * kParts * n_acc_rows * (E / 4 + 1) * 4 * sizeof(float);
+}
+
+extern "C" int danet_anchor_num_subsets(int n_anchor, int C) { return n_choose_k(n_anchor, C); }
+
+extern "C" int danet_attractor_truth_fwd(const float* embed, const float* src_pwr, const float* mix_pwr,
+                                         float* attractors, int B, int C, int TF, int E, int mode,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("attractor_truth", embed, B, C, TF, E, C, workspace, workspace_bytes);
+  if (rc) return rc;
+  DANET_REQUIRE(src_pwr && attractors, DANET_E_ARG, "attractor_truth: null pointer");
+  DANET_REQUIRE(mode >= 0 && mode <= 2, DANET_E_ARG, "attractor_truth: mode %d", mode);
+  DANET_REQUIRE(mode == 0 || mix_pwr, DANET_E_ARG, "attractor_truth: mode %d needs mix_pwr", mode);
+  if (B == 0) return DANET_OK;
+  AttParams p = {};
+  p.embed = embed; p.src_pwr = src_pwr; p.mix_pwr = mix_pwr; p.aux = nullptr;
+  p.part = reinterpret_cast<float*>(workspace);
+  p.TF = TF; p.C = C; p.E = E; p.R = C; p.nQ = E / 4 + 1; p.ldv = quad_stride(E); p.truth_mode = mode;
+  rc = launch_partial<MODE_TRUTH>(p, B, 0, as_stream(stream));
+  if (rc) return rc;
+  attractor_finalize_kernel<MODE_TRUTH><<<B, 256, 0, as_stream(stream)>>>(
+      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* anchors, float* attractors,
+                                          float* attractor_sets, float* similarities, int* choice,
+                                          int B, int C, int TF, int E, int n_anchor, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  DANET_REQUIRE(n_anchor >= C && n_anchor <= kMaxAnchor, DANET_E_SHAPE,
+                "attractor_anchor: n_anchor %d (C %d .. %d)", n_anchor, C, kMaxAnchor);
+  const int P = n_choose_k(n_anchor, C);
+  DANET_REQUIRE(P >= 1 && P <= 20, DANET_E_SHAPE, "attractor_anchor: %d subsets (max 20)", P);
+  int rc = check_common("attractor_anchor", embed, B, C, TF, E, P * C, workspace, workspace_bytes);
+  if (rc) return rc;
+  DANET_REQUIRE(anchors && attractors, DANET_E_ARG, "attractor_anchor: null pointer");
+  if (B == 0) return DANET_OK;
+  AttParams p = {};
+  p.embed = embed; p.aux = anchors; p.part = reinterpret_cast<float*>(workspace);
+  p.TF = TF; p.C = C; p.E = E; p.R = P * C; p.nQ = E / 4 + 1; p.ldv = quad_stride(E);
+  p.n_anchor = n_anchor; p.n_sub = P;
+  {   // itertools.combinations order (app/ops.py:287-290)
+    int idx[kAttMaxC];
+    for (int c = 0; c < C; ++c) idx[c] = c;
+    for (int s = 0; s < P; ++s) {
+      for (int c = 0; c < C; ++c) p.subsets[s * kAttMaxC + c] = idx[c];
+      int i = C - 1;
+      while (i >= 0 && idx[i] == n_anchor - C + i) --i;
+      if (i < 0) break;
+      ++idx[i];
+      for (int j = i + 1; j < C; ++j) idx[j] = idx[j - 1] + 1;
+    }
+  }
+  rc = launch_partial<MODE_ANCHOR>(p, B, n_anchor * E, as_stream(stream));
+  if (rc) return rc;
+  attractor_finalize_kernel<MODE_ANCHOR><<<B, 256, 0, as_stream(stream)>>>(
+      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_attractor_kmeans_fwd(const float* embed, float* centroids, int B, int C, int TF,
+                                          int E, int n_iter, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  int rc = check_common("attractor_kmeans", embed, B, C, TF, E, C, workspace, workspace_bytes);
+  if (rc) return rc;
+  DANET_REQUIRE(centroids && n_iter >= 0, DANET_E_ARG, "attractor_kmeans: centroids %p n_iter %d",
+                (void*)centroids, n_iter);
+  if (B == 0) return DANET_OK;
+  AttParams p = {};
+  p.embed = embed; p.aux = centroids; p.part = reinterpret_cast<float*>(workspace);
+  p.TF = TF; p.C = C; p.E = E; p.R = C; p.nQ = E / 4 + 1; p.ldv = quad_stride(E);
+  for (int it = 0; it < n_iter; ++it) {
+    rc = launch_partial<MODE_KMEANS>(p, B, C * E, as_stream(stream));
+    if (rc) return rc;
+    attractor_finalize_kernel<MODE_KMEANS><<<B, 256, 0, as_stream(stream)>>>(
+        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr);
+    DANET_LAUNCH_CHECK();
+  }
+  return DANET_OK;
+}

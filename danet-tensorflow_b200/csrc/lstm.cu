@@ -1,0 +1,212 @@
+// K2b: (Bi)LSTM sequence kernel -- Model.lyr_lstm (main.py:76-132, tf.scan from zero
+// state) over ops.lyr_lstm_flat (app/ops.py:139-147) and _lyr_bilstm (app/modules.py:120-137).
+//   a = pre_t + h_{t-1} * Wh ; g = a[0:H] (NO tanh) ; i,f,o = sigmoid(a[H:4H])
+//   c_t = i*g + f*c_{t-1} ; h_t = o*tanh(c_t) ; direction 1 walks t = T-1 .. 0.
+// backend 0 (this file): persistent fp32 kernel.  One CTA owns 8 hidden units (their 4
+// gate columns of Wh stay in shared memory for the whole sequence) of 16 utterances of one
+// direction; the CTAs of one (direction, batch tile) group exchange h_t through L2 (the
+// output tensor itself) and a release/acquire counter.  Launched cooperatively so every
+// CTA of a group is resident.  backend 1: tcgen05 cluster kernel (lstm_tc.cu).
+#include "common.cuh"
+
+namespace danet {
+
+int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out,
+                float* cell_seq, int n_dir, int T, int B, int H, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
+
+constexpr int kU = 8;      // hidden units per CTA
+constexpr int kBt = 16;    // utterances per CTA
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct LstmSeqParams {
+  const float* pre;        // [n_dir][T][B][4H]
+  const float* Wh[2];      // recurrent rows [H][4H] (row stride ldw)
+  long long ldw;
+  float* out;              // [B][T][n_dir*H]
+  float* cell_seq;         // nullable [n_dir][T][B][H]
+  int* counters;           // [n_dir][n_bt_total]
+  int n_dir, T, B, H;
+  int bt0;                 // first batch tile of this launch
+  int n_bt_total;
+};
+
+__global__ void __launch_bounds__(256)
+lstm_seq_kernel(LstmSeqParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, T = p.T, B = p.B;
+  const int ldh = H + 4;
+  float4* Ws = reinterpret_cast<float4*>(smem);            // [H][kU] float4 = 4 gates
+  float* hs = smem + (size_t)H * kU * 4;                   // [kBt][ldh]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int n_chunks = gridDim.x;
+  const int u0 = chunk * kU, b0 = bt * kBt;
+
+  // stage this CTA's slice of Wh: Ws[k][u] = (W[k][0H+u0+u], W[k][1H+..], W[k][2H+..], W[k][3H+..])
+  const float* Wg = p.Wh[dir];
+  for (int i = tid; i < H * kU; i += 256) {
+    const int k = i / kU, u = i % kU, unit = u0 + u;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (unit < H) {
+      const float* r = Wg + (size_t)k * p.ldw + unit;
+      w = make_float4(__ldg(r), __ldg(r + H), __ldg(r + 2 * H), __ldg(r + 3 * H));
+    }
+    Ws[i] = w;
+  }
+  for (int i = tid; i < kBt * ldh; i += 256) hs[i] = 0.f;   // h_{-1} = 0 (main.py:112-121)
+
+  const int pi = warp * 16 + (lane & 15);    // (utterance, unit) pair, two k-halves per pair
+  const int khalf = lane >> 4;
+  const int bl = pi / kU, u = pi % kU;
+  const int b = b0 + bl, unit = u0 + u;
+  const bool valid = b < B && unit < H;
+  const int kmid = ((H / 2 + 3) / 4) * 4;
+  const int kbeg = khalf ? kmid : 0, kend = khalf ? H : kmid;
+  const int outw = p.n_dir * H;
+  int* counter = p.counters + dir * p.n_bt_total + bt;
+
+  float c = 0.f;
+  float pre_next[4] = {0.f, 0.f, 0.f, 0.f};
+  auto load_pre = [&](int s, float (&dst)[4]) {
+    if (valid && khalf == 0 && s < T) {
+      const int to = dir ? T - 1 - s : s;
+      const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dst[g] = __ldg(q + g * H);
+    }
+  };
+  load_pre(0, pre_next);
+  __syncthreads();
+
+  for (int s = 0; s < T; ++s) {
+    const int to = dir ? T - 1 - s : s;
+    float pre_cur[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pre_cur[g] = pre_next[g];
+    load_pre(s + 1, pre_next);
+    if (s > 0) {
+      // wait until every CTA of this (direction, batch tile) group has published h_{s-1}
+      if (tid == 0) {
+        const int want = n_chunks * s;
+        while (ld_acquire(counter) < want) {}
+      }
+      __syncthreads();
+      const int tp = dir ? to + 1 : to - 1;
+      const int nq = H / 4;
+      for (int i = tid; i < kBt * nq; i += 256) {
+        const int r = i / nq, q = i % nq;
+        if (b0 + r < B) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(
+              p.out + ((size_t)(b0 + r) * T + tp) * outw + dir * H) + q);
+          *reinterpret_cast<float4*>(hs + r * ldh + 4 * q) = v;
+        }
+      }
+      __syncthreads();
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    {
+      const float* hr = hs + bl * ldh;
+#pragma unroll 2
+      for (int k = kbeg; k < kend; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hr + k);
+        const float4 w0 = Ws[(k + 0) * kU + u], w1 = Ws[(k + 1) * kU + u];
+        const float4 w2 = Ws[(k + 2) * kU + u], w3 = Ws[(k + 3) * kU + u];
+        a0 = fmaf(hv.x, w0.x, a0); a1 = fmaf(hv.x, w0.y, a1); a2 = fmaf(hv.x, w0.z, a2); a3 = fmaf(hv.x, w0.w, a3);
+        a0 = fmaf(hv.y, w1.x, a0); a1 = fmaf(hv.y, w1.y, a1); a2 = fmaf(hv.y, w1.z, a2); a3 = fmaf(hv.y, w1.w, a3);
+        a0 = fmaf(hv.z, w2.x, a0); a1 = fmaf(hv.z, w2.y, a1); a2 = fmaf(hv.z, w2.z, a2); a3 = fmaf(hv.z, w2.w, a3);
+        a0 = fmaf(hv.w, w3.x, a0); a1 = fmaf(hv.w, w3.y, a1); a2 = fmaf(hv.w, w3.z, a2); a3 = fmaf(hv.w, w3.w, a3);
+      }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+    if (valid && khalf == 0) {
+      const float g = a0 + pre_cur[0];
+      const float ig = sigmoidf_(a1 + pre_cur[1]);
+      const float fg = sigmoidf_(a2 + pre_cur[2]);
+      const float og = sigmoidf_(a3 + pre_cur[3]);
+      c = ig * g + fg * c;
+      const float h = og * tanhf(c);
+      __stcg(p.out + ((size_t)b * T + to) * outw + dir * H + unit, h);
+      if (p.cell_seq) p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit] = c;
+    }
+    __syncthreads();   // all h_s stores of this CTA issued; hs free for the next step
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(counter, 1);
+    }
+  }
+}
+
+static size_t lstm_smem_bytes(int H) { return ((size_t)H * kU * 4 + (size_t)kBt * (H + 4)) * sizeof(float); }
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H) {
+  if (n_dir < 1 || B < 1 || H < 1) return 256;
+  size_t simt = (((size_t)n_dir * ((B + kBt - 1) / kBt) * sizeof(int)) + 255) / 256 * 256;
+  size_t tc = lstm_tc_workspace_bytes(n_dir, B, H);
+  return simt > tc ? simt : tc;
+}
+
+extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
+                                  float* out, float* cell_seq, int n_dir, int T, int B, int H,
+                                  void* workspace, size_t workspace_bytes, int backend,
+                                  void* stream) {
+  DANET_REQUIRE(pre && host_Wh && out && workspace, DANET_E_ARG, "lstm_seq: null pointer");
+  DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_seq: n_dir %d", n_dir);
+  for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_seq: null Wh[%d]", d);
+  DANET_REQUIRE(T >= 0 && B >= 0 && H >= 4 && H % 4 == 0 && ldw >= 4ll * H, DANET_E_SHAPE,
+                "lstm_seq: T %d B %d H %d (multiple of 4) ldw %lld", T, B, H, ldw);
+  DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq: backend %d", backend);
+  DANET_REQUIRE(aligned16(out), DANET_E_ALIGN, "lstm_seq: out must be 16-byte aligned");
+  DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
+                "lstm_seq: workspace %zu < %zu", workspace_bytes,
+                danet_lstm_seq_workspace_bytes(n_dir, B, H));
+  if (T == 0 || B == 0) return DANET_OK;
+  cudaStream_t st = as_stream(stream);
+  if (backend == 1)
+    return lstm_tc_fwd(pre, host_Wh, ldw, out, cell_seq, n_dir, T, B, H, workspace, workspace_bytes, st);
+
+  const size_t smem = lstm_smem_bytes(H);
+  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: H %d needs %zu B of shared memory", H, smem);
+  DANET_CUDA(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_kernel, 256, smem));
+  const int n_chunks = (H + kU - 1) / kU;
+  const int n_bt = (B + kBt - 1) / kBt;
+  const int resident = per_sm * num_sms();
+  int bt_per_launch = resident / (n_dir * n_chunks);
+  DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE,
+                "lstm_seq: one batch tile needs %d resident CTAs, device holds %d", n_dir * n_chunks, resident);
+  if (bt_per_launch > n_bt) bt_per_launch = n_bt;
+  DANET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_dir * n_bt * sizeof(int), st));
+  LstmSeqParams p;
+  p.pre = pre;
+  p.Wh[0] = host_Wh[0];
+  p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
+  p.ldw = ldw;
+  p.out = out;
+  p.cell_seq = cell_seq;
+  p.counters = reinterpret_cast<int*>(workspace);
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
+  p.n_bt_total = n_bt;
+  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
+    p.bt0 = bt0;
+    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
+    void* args[] = {&p};
+    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(n_chunks, nb, n_dir),
+                                           dim3(256), args, smem, st));
+  }
+  return DANET_OK;
+}

@@ -12,7 +12,8 @@ constexpr int kMaxE = 128;
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
 mask_cmul_kernel(const float* __restrict__ embed, const float* __restrict__ attractors,
-                 const float2* __restrict__ mix, float* __restrict__ sep_pwr,
+                 const float2* __restrict__ mix, const float* __restrict__ mix_pwr,
+                 float* __restrict__ sep_pwr,
                  float2* __restrict__ sep, float* __restrict__ masks, int C, long long TF, int E,
                  int kind) {
   __shared__ float s_att[kMaxC * kMaxE];
@@ -70,8 +71,14 @@ mask_cmul_kernel(const float* __restrict__ embed, const float* __restrict__ attr
       for (int c = 0; c < kMaxC; ++c)
         if (c < C) m[c] = sigmoidf_(logit[c]);
     }
-    const float2 z = __ldg(mix + (size_t)b * TF + i);
-    const float p = sqrtf(z.x * z.x + z.y * z.y);
+    float2 z = make_float2(0.f, 0.f);
+    float p;
+    if (mix) {
+      z = __ldg(mix + (size_t)b * TF + i);
+      p = mix_pwr ? __ldg(mix_pwr + (size_t)b * TF + i) : sqrtf(z.x * z.x + z.y * z.y);
+    } else {
+      p = __ldg(mix_pwr + (size_t)b * TF + i);
+    }
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c)
       if (c < C) {
@@ -88,9 +95,10 @@ mask_cmul_kernel(const float* __restrict__ embed, const float* __restrict__ attr
 using namespace danet;
 
 extern "C" int danet_mask_cmul_fwd(const float* embed, const float* attractors, const float* mix_c64,
-                                   float* sep_pwr, float* sep_c64, float* masks, int B, int C, int TF,
+                                   const float* mix_pwr, float* sep_pwr, float* sep_c64, float* masks, int B, int C, int TF,
                                    int E, int kind, void* stream) {
-  DANET_REQUIRE(embed && attractors && mix_c64, DANET_E_ARG, "mask_cmul: null pointer");
+  DANET_REQUIRE(embed && attractors && (mix_c64 || mix_pwr), DANET_E_ARG, "mask_cmul: null pointer");
+  DANET_REQUIRE(mix_c64 || !sep_c64, DANET_E_ARG, "mask_cmul: complex output needs the complex mixture");
   DANET_REQUIRE(B >= 0 && TF >= 0 && C >= 1 && C <= kMaxC && E >= 1 && E <= kMaxE, DANET_E_SHAPE,
                 "mask_cmul: B %d C %d (<=%d) TF %d E %d (<=%d)", B, C, kMaxC, TF, E, kMaxE);
   DANET_REQUIRE(kind == 0 || kind == 1, DANET_E_ARG, "mask_cmul: kind %d", kind);
@@ -105,9 +113,9 @@ extern "C" int danet_mask_cmul_fwd(const float* embed, const float* attractors, 
   auto mixp = reinterpret_cast<const float2*>(mix_c64);
   auto sepp = reinterpret_cast<float2*>(sep_c64);
   if (vec)
-    mask_cmul_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(embed, attractors, mixp, sep_pwr, sepp, masks, C, TF, E, kind);
+    mask_cmul_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(embed, attractors, mixp, mix_pwr, sep_pwr, sepp, masks, C, TF, E, kind);
   else
-    mask_cmul_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(embed, attractors, mixp, sep_pwr, sepp, masks, C, TF, E, kind);
+    mask_cmul_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(embed, attractors, mixp, mix_pwr, sep_pwr, sepp, masks, C, TF, E, kind);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }

@@ -1,0 +1,320 @@
+"""
+Torch-tensor front of the C-ABI (include/danet.h).  PyTorch is plumbing here: it owns
+device memory and the stream; every computation is a call into libdanet_sm100.so with raw
+device pointers.  Argument problems raise ValueError, device problems RuntimeError.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+FEATURE = 129
+FFT_SIZE = 256
+FFT_STRIDE = 64
+
+# 0 = exact fp32 SIMT kernels, 1 = tcgen05 (bf16x3 split operands, fp32 accumulate)
+DEFAULT_BACKEND = int(os.environ.get('DANET_BACKEND', '1'))
+
+# launch counter: bench.py reports how many of OUR kernels ran inside the timed region
+launches = 0
+
+
+def _count(n=1):
+    global launches
+    launches += n
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, name, dtype=torch.float32, dim=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError('%s: expected a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise ValueError('%s: expected a CUDA tensor (there is no CPU path)' % name)
+    if t.dtype != dtype:
+        raise ValueError('%s: expected dtype %s, got %s' % (name, dtype, t.dtype))
+    if dim is not None and t.dim() != dim:
+        raise ValueError('%s: expected %d dims, got shape %s' % (name, dim, tuple(t.shape)))
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def num_frames(n_samples):
+    """T = ceil(N/64) + 1 (scipy.signal.stft padding as used at app/utils.py:117-122)"""
+    t = _lib.load().danet_stft_num_frames(int(n_samples))
+    if t < 0:
+        raise ValueError('window is longer than input signal (%d < 256)' % n_samples)
+    return t
+
+
+def stft(wav, want_logmag=False):
+    """wav f32 [..., N] -> spec c64 [..., T, 129] (+ log1p|spec| f32)   [app/utils.py:117-122]"""
+    wav = _req(wav, 'wav')
+    lead, n = wav.shape[:-1], wav.shape[-1]
+    T = num_frames(n)
+    n_sig = int(torch.Size(lead).numel())
+    spec = torch.empty(lead + (T, FEATURE), dtype=torch.complex64, device=wav.device)
+    logmag = torch.empty(lead + (T, FEATURE), dtype=torch.float32, device=wav.device) if want_logmag else None
+    _lib.check(_lib.load().danet_stft_fwd(_p(wav), n_sig, n, _p(spec), _p(logmag), _stream()), 'stft')
+    _count()
+    return (spec, logmag) if want_logmag else spec
+
+
+def istft(spec):
+    """spec c64 [..., T, 129] -> wav f32 [..., 64*T] with utils.istft semantics [app/utils.py:53-75]"""
+    spec = _req(spec, 'spec', torch.complex64)
+    if spec.dim() < 2 or spec.shape[-1] != FEATURE:
+        raise ValueError('spec: expected [..., T, 129], got %s' % (tuple(spec.shape),))
+    lead, T = spec.shape[:-2], spec.shape[-2]
+    n_sig = int(torch.Size(lead).numel())
+    wav = torch.empty(lead + (FFT_STRIDE * T,), dtype=torch.float32, device=spec.device)
+    _lib.check(_lib.load().danet_istft_fwd(_p(spec), n_sig, T, _p(wav), _stream()), 'istft')
+    _count()
+    return wav
+
+
+def mix_features(src, want=('mix', 'src_pwr', 'mix_pwr', 'logmag')):
+    """src c64 [B,C,T,F] -> dict(mix c64 [B,T,F], src_pwr [B,C,T,F], mix_pwr, logmag [B,T,F])
+    [main.py:233-240]"""
+    src = _req(src, 'src', torch.complex64, 4)
+    B, Cn, T, F = src.shape
+    dev = src.device
+    out = {
+        'mix': torch.empty((B, T, F), dtype=torch.complex64, device=dev) if 'mix' in want else None,
+        'src_pwr': torch.empty((B, Cn, T, F), dtype=torch.float32, device=dev) if 'src_pwr' in want else None,
+        'mix_pwr': torch.empty((B, T, F), dtype=torch.float32, device=dev) if 'mix_pwr' in want else None,
+        'logmag': torch.empty((B, T, F), dtype=torch.float32, device=dev) if 'logmag' in want else None,
+    }
+    _lib.check(_lib.load().danet_mix_features_fwd(
+        _p(src), B, Cn, T * F, _p(out['mix']), _p(out['src_pwr']), _p(out['mix_pwr']), _p(out['logmag']),
+        _stream()), 'mix_features')
+    _count()
+    return out
+
+
+def center(x, out=None):
+    """x [B, ...] minus its per-utterance mean over all other axes [app/modules.py:209-210, 244-245]"""
+    x = _req(x, 'x')
+    B = x.shape[0]
+    n_per = x[0].numel() if B else 1
+    y = torch.empty_like(x) if out is None else out
+    lib = _lib.load()
+    ws = _ws(lib.danet_center_workspace_bytes(B), x.device)
+    _lib.check(lib.danet_center_fwd(_p(x), B, n_per, _p(y), _p(ws), _stream()), 'center')
+    _count(2)
+    return y
+
+
+def linear(a, w, bias=None, time_major_T=0, backend=None, k_rows=None, row_offset=0, out=None):
+    """
+    a [M,K] @ w[row_offset : row_offset+K, :] (+ bias) -> [M,N]   [app/ops.py:72-89]
+    `w` is the reference's stacked [I+H, 4H] matrix or a plain [K,N]; rows are selected without
+    a copy.  time_major_T > 0 writes logical row b*T+t to row t*(M/T)+b.
+    """
+    a = _req(a, 'a', dim=2)
+    w = _req(w, 'w', dim=2)
+    M, K = a.shape
+    N = w.shape[1]
+    if k_rows is None:
+        k_rows = w.shape[0] - row_offset
+    if k_rows != K or row_offset + K > w.shape[0]:
+        raise ValueError('linear: a is [%d,%d] but w rows %d..%d of %d' % (M, K, row_offset, row_offset + k_rows, w.shape[0]))
+    if bias is not None:
+        bias = _req(bias, 'bias', dim=1)
+        if bias.shape[0] != N:
+            raise ValueError('linear: bias has %d entries, N = %d' % (bias.shape[0], N))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    elif tuple(out.shape) != (M, N) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError('linear: out must be a contiguous float32 [%d,%d]' % (M, N))
+    wp = C.c_void_p(w.data_ptr() + row_offset * N * 4)
+    be = DEFAULT_BACKEND if backend is None else backend
+    _lib.check(_lib.load().danet_linear_fwd(_p(a), K, wp, N, _p(bias), _p(out), M, N, K, int(time_major_T),
+                                            be, _stream()), 'linear')
+    _count()
+    return out
+
+
+def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False):
+    """
+    pre [n_dir,T,B,4H]; w_list = the reference's stacked [I+H,4H] matrices, one per direction
+    (recurrent rows start at `in_dim`) -> hidden [B,T,n_dir*H] (+ cell [n_dir,T,B,H])
+    [main.py:76-132; app/ops.py:139-147; app/modules.py:120-137]
+    """
+    pre = _req(pre, 'pre', dim=4)
+    n_dir = len(w_list)
+    if tuple(pre.shape) != (n_dir, T, B, 4 * H):
+        raise ValueError('lstm_seq: pre is %s, expected %s' % (tuple(pre.shape), (n_dir, T, B, 4 * H)))
+    ptrs = (C.c_void_p * n_dir)()
+    keep = []
+    for d, w in enumerate(w_list):
+        w = _req(w, 'W[%d]' % d, dim=2)
+        if tuple(w.shape) != (in_dim + H, 4 * H):
+            raise ValueError('lstm_seq: W[%d] is %s, expected %s' % (d, tuple(w.shape), (in_dim + H, 4 * H)))
+        keep.append(w)
+        ptrs[d] = w.data_ptr() + in_dim * 4 * H * 4
+    out = torch.empty((B, T, n_dir * H), dtype=torch.float32, device=pre.device)
+    cell = torch.empty((n_dir, T, B, H), dtype=torch.float32, device=pre.device) if keep_cell else None
+    lib = _lib.load()
+    nws = lib.danet_lstm_seq_workspace_bytes(n_dir, B, H)
+    ws = _ws(nws, pre.device)
+    be = DEFAULT_BACKEND if backend is None else backend
+    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), ptrs, 4 * H, _p(out), _p(cell), n_dir, T, B, H, _p(ws),
+                                      ws.numel(), be, _stream()), 'lstm_seq')
+    _count()
+    return (out, cell) if keep_cell else out
+
+
+def _embed_flat(embed):
+    embed = _req(embed, 'embed')
+    if embed.dim() == 4:
+        B, T, F, E = embed.shape
+        return embed, B, T * F, E
+    if embed.dim() == 3:
+        B, TF, E = embed.shape
+        return embed, B, TF, E
+    raise ValueError('embed: expected [B,T,F,E] or [B,T*F,E], got %s' % (tuple(embed.shape),))
+
+
+TRUTH_MODES = {'truth': 0, 'truth-threshold': 1, 'truth-weighted': 2}
+
+
+def attractor_truth(embed, src_pwr, mix_pwr, mode):
+    """[app/modules.py:390-412 / 425-450 / 462-487] -> [B,C,E]"""
+    embed, B, TF, E = _embed_flat(embed)
+    src_pwr = _req(src_pwr, 'src_pwr', dim=4)
+    Cn = src_pwr.shape[1]
+    if src_pwr.shape[0] != B or src_pwr.shape[2] * src_pwr.shape[3] != TF:
+        raise ValueError('attractor_truth: src_pwr %s does not match embed' % (tuple(src_pwr.shape),))
+    m = TRUTH_MODES[mode] if isinstance(mode, str) else int(mode)
+    if m != 0:
+        mix_pwr = _req(mix_pwr, 'mix_pwr', dim=3)
+        if mix_pwr.shape[0] != B or mix_pwr.shape[1] * mix_pwr.shape[2] != TF:
+            raise ValueError('attractor_truth: mix_pwr %s does not match embed' % (tuple(mix_pwr.shape),))
+    else:
+        mix_pwr = None
+    out = torch.empty((B, Cn, E), dtype=torch.float32, device=embed.device)
+    lib = _lib.load()
+    ws = _ws(lib.danet_attractor_workspace_bytes(B, Cn, E), embed.device)
+    _lib.check(lib.danet_attractor_truth_fwd(_p(embed), _p(src_pwr), _p(mix_pwr), _p(out), B, Cn, TF, E, m,
+                                             _p(ws), ws.numel(), _stream()), 'attractor_truth')
+    _count(2)
+    return out
+
+
+def attractor_anchor(embed, anchors, n_signal, return_all=False):
+    """[app/modules.py:501-545] -> [B,C,E] (+ sets [B,P,C,E], sims [B,P], choice [B] int32)"""
+    embed, B, TF, E = _embed_flat(embed)
+    anchors = _req(anchors, 'anchors', dim=2)
+    A = anchors.shape[0]
+    if anchors.shape[1] != E:
+        raise ValueError('attractor_anchor: anchors %s, E = %d' % (tuple(anchors.shape), E))
+    lib = _lib.load()
+    P = lib.danet_anchor_num_subsets(A, n_signal)
+    dev = embed.device
+    out = torch.empty((B, n_signal, E), dtype=torch.float32, device=dev)
+    sets = torch.empty((B, P, n_signal, E), dtype=torch.float32, device=dev) if return_all else None
+    sims = torch.empty((B, P), dtype=torch.float32, device=dev) if return_all else None
+    choice = torch.empty((B,), dtype=torch.int32, device=dev) if return_all else None
+    ws = _ws(lib.danet_attractor_workspace_bytes(B, max(P, 1) * n_signal, E), dev)
+    _lib.check(lib.danet_attractor_anchor_fwd(_p(embed), _p(anchors), _p(out), _p(sets), _p(sims), _p(choice),
+                                              B, n_signal, TF, E, A, _p(ws), ws.numel(), _stream()),
+               'attractor_anchor')
+    _count(2)
+    return (out, sets, sims, choice) if return_all else out
+
+
+def attractor_kmeans(embed, init, n_iter=5):
+    """Lloyd iterations from `init` [B,C,E] (new plugin, no reference twin) -> [B,C,E]"""
+    embed, B, TF, E = _embed_flat(embed)
+    cen = _req(init, 'init', dim=3).clone()
+    if cen.shape[0] != B or cen.shape[2] != E:
+        raise ValueError('attractor_kmeans: init %s does not match embed' % (tuple(cen.shape),))
+    Cn = cen.shape[1]
+    lib = _lib.load()
+    ws = _ws(lib.danet_attractor_workspace_bytes(B, Cn, E), embed.device)
+    _lib.check(lib.danet_attractor_kmeans_fwd(_p(embed), _p(cen), B, Cn, TF, E, int(n_iter), _p(ws),
+                                              ws.numel(), _stream()), 'attractor_kmeans')
+    _count(2 * int(n_iter))
+    return cen
+
+
+SEPARATOR_KINDS = {'dot-softmax-orig': 0, 'dot-sigmoid-orig': 1}
+
+
+def mask_cmul(embed, attractors, mix, kind, want=('sep_pwr', 'sep', 'masks'), mix_pwr=None):
+    """
+    [app/modules.py:548-603; main.py:281-284] embed [B,TF,E], attractors [B,C,E], mix c64 [B,T,F]
+    and/or mix_pwr f32 [B,T,F] -> dict(sep_pwr [B,C,T,F], sep c64 [B,C,T,F], masks [B,T,F,C])
+    """
+    embed, B, TF, E = _embed_flat(embed)
+    attractors = _req(attractors, 'attractors', dim=3)
+    if mix is None and mix_pwr is None:
+        raise ValueError('mask_cmul: need the complex mixture or its magnitude')
+    if mix is not None:
+        mix = _req(mix, 'mix', torch.complex64, 3)
+    if mix_pwr is not None:
+        mix_pwr = _req(mix_pwr, 'mix_pwr', dim=3)
+    if mix is None:
+        want = tuple(w for w in want if w != 'sep')
+    Cn = attractors.shape[1]
+    if attractors.shape[0] != B or attractors.shape[2] != E:
+        raise ValueError('mask_cmul: attractors %s do not match embed' % (tuple(attractors.shape),))
+    for nm, m in (('mix', mix), ('mix_pwr', mix_pwr)):
+        if m is not None and (m.shape[0] != B or m.shape[1] * m.shape[2] != TF):
+            raise ValueError('mask_cmul: %s %s does not match embed' % (nm, tuple(m.shape)))
+    T, F = (mix if mix is not None else mix_pwr).shape[1:]
+    dev = embed.device
+    k = SEPARATOR_KINDS[kind] if isinstance(kind, str) else int(kind)
+    out = {
+        'sep_pwr': torch.empty((B, Cn, T, F), dtype=torch.float32, device=dev) if 'sep_pwr' in want else None,
+        'sep': torch.empty((B, Cn, T, F), dtype=torch.complex64, device=dev) if 'sep' in want else None,
+        'masks': torch.empty((B, T, F, Cn), dtype=torch.float32, device=dev) if 'masks' in want else None,
+    }
+    _lib.check(_lib.load().danet_mask_cmul_fwd(_p(embed), _p(attractors), _p(mix), _p(mix_pwr), _p(out['sep_pwr']),
+                                               _p(out['sep']), _p(out['masks']), B, Cn, TF, E, k, _stream()),
+               'mask_cmul')
+    _count()
+    return out
+
+
+def pit_mse(x, y):
+    """
+    [app/ops.py:374-431, 191-222; main.py:293-309]  x, y [B,C,T,F] both complex64 or both float32
+    -> dict(loss [1], perm_idx [B] int32, perm_losses [B,C!], cross [B,C,C], snr [B])
+    """
+    cplx = x.dtype == torch.complex64
+    x = _req(x, 'x', torch.complex64 if cplx else torch.float32, 4)
+    y = _req(y, 'y', torch.complex64 if cplx else torch.float32, 4)
+    if x.shape != y.shape:
+        raise ValueError('pit_mse: shapes differ %s vs %s' % (tuple(x.shape), tuple(y.shape)))
+    B, Cn, T, F = x.shape
+    nperm = 1
+    for c in range(2, Cn + 1):
+        nperm *= c
+    dev = x.device
+    out = {
+        'cross': torch.empty((B, Cn, Cn), dtype=torch.float32, device=dev),
+        'perm_losses': torch.empty((B, nperm), dtype=torch.float32, device=dev),
+        'perm_idx': torch.empty((B,), dtype=torch.int32, device=dev),
+        'loss': torch.empty((1,), dtype=torch.float32, device=dev),
+        'snr': torch.empty((B,), dtype=torch.float32, device=dev),
+    }
+    lib = _lib.load()
+    ws = _ws(lib.danet_pit_workspace_bytes(B, Cn), dev)
+    _lib.check(lib.danet_pit_mse_fwd(_p(x), _p(y), B, Cn, T * F, 1 if cplx else 0, _p(out['cross']),
+                                     _p(out['perm_losses']), _p(out['perm_idx']), _p(out['loss']),
+                                     _p(out['snr']), _p(ws), ws.numel(), _stream()), 'pit_mse')
+    _count(2)
+    return out

@@ -1,0 +1,194 @@
+"""
+Model assembly -- the role of the reference's `Model` (main.py:61-399) without a graph:
+`build()` instantiates the registered Encoder / Estimator / Separator plugins,
+`train_forward` / `valid_forward` / `infer` run what one `sess.run` of the matching fetch
+list computes (main.py:369-397), `separate` is the demo path wav -> wavs
+(main.py:660-695 + app/utils.py:111-135).  Variables live in `self.params` under the
+reference's TF names so checkpoints are interchangeable by name.
+"""
+import itertools
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from . import modules as _modules   # noqa: F401  (registers the plugins, like app/__init__.py:1-5)
+from .hparams import hparams
+
+
+class Model(object):
+    def __init__(self, name='danet', device='cuda:0', seed=1337):
+        self.name = name
+        self.device = torch.device(device)
+        self.params = {}                  # reference variable name (without 'global/') -> tensor
+        self._rs = np.random.RandomState(seed)
+        self.encoder = None
+        self.estimator = None
+        self.infer_estimator = None
+        self.separator = None
+        self.s_states_di = {}             # main.py:110-121 -- zero state, never assigned
+
+    # ---------------------------------------------------------------- variables
+    def get_variable(self, name, shape, init):
+        """tf.get_variable with reuse: created on first use, in call order, from one RandomState
+        stream (same stream as the golden fixtures' weights)."""
+        v = self.params.get(name)
+        if v is None:
+            a = np.ascontiguousarray(np.asarray(init(self._rs, list(shape)), dtype=np.float32))
+            if list(a.shape) != list(shape):
+                raise ValueError('initialiser for %s returned %s, wanted %s' % (name, a.shape, shape))
+            v = torch.from_numpy(a).to(self.device)
+            self.params[name] = v
+        elif list(v.shape) != list(shape):
+            raise ValueError('variable %s has shape %s, requested %s' % (name, tuple(v.shape), shape))
+        return v
+
+    def load_params(self, params):
+        """Take weights by reference name (numpy arrays or tensors); the role of main.py:201-206"""
+        for k, v in params.items():
+            t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
+            self.params[k] = t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def save_params(self, path):
+        """main.py:192-199 -- trainable variables only (no optimiser slots)"""
+        torch.save({k: v.cpu() for k, v in self.params.items()}, path)
+
+    def parameter_count(self):
+        return sum(int(v.numel()) for v in self.params.values())
+
+    # ---------------------------------------------------------------- recurrent layers
+    def _lstm_vars(self, name, idim, hdim, w_init, b_init):
+        W = self.get_variable(name + '/LSTM/linear/W', [idim + hdim, 4 * hdim], w_init)
+        Bv = self.get_variable(name + '/LSTM/linear/B', [4 * hdim], b_init)
+        return W, Bv
+
+    def lyr_lstm(self, name, s_x, hdim, axis=-1, t_axis=0, op_linear=None, w_init=None, b_init=None,
+                 reverse=False):
+        """main.py:76-132: one direction over [B,T,I] from zero state -> [B,T,hdim].
+        The layer is `hoisted input GEMM for all t` + `persistent recurrent kernel`."""
+        B, T, I = s_x.shape
+        W, Bv = self._lstm_vars(name, I, hdim, w_init, b_init)
+        x2 = s_x.reshape(B * T, I)
+        pre = K.linear(x2, W, Bv, time_major_T=T, k_rows=I).view(1, T, B, 4 * hdim)
+        if reverse:
+            raise NotImplementedError('single reversed direction: use lyr_bilstm')
+        return K.lstm_seq(pre, [W], I, T, B, hdim)
+
+    def lyr_bilstm(self, name, s_x, hdim, w_init=None, b_init=None):
+        """app/modules.py:120-137 in one launch: [B,T,I] -> [B,T,2*hdim] (fwd | bwd un-reversed)"""
+        B, T, I = s_x.shape
+        Wf, Bf = self._lstm_vars(name + '_fwd', I, hdim, w_init, b_init)
+        Wb, Bb = self._lstm_vars(name + '_bwd', I, hdim, w_init, b_init)
+        x2 = s_x.reshape(B * T, I)
+        pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
+        K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
+        K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))
+        return K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
+
+    # ---------------------------------------------------------------- assembly
+    def build(self):
+        """main.py:208-278: pick the plugins; variables appear on first call, in the reference's
+        creation order (encoder, train_estimator, infer_estimator)."""
+        self.encoder = hparams.get_encoder()(self, 'encoder')
+        self.estimator = hparams.get_estimator(hparams.TRAIN_ESTIMATOR_METHOD)(self, 'train_estimator')
+        if hparams.INFER_ESTIMATOR_METHOD != hparams.TRAIN_ESTIMATOR_METHOD:
+            self.infer_estimator = hparams.get_estimator(hparams.INFER_ESTIMATOR_METHOD)(self, 'infer_estimator')
+            if self.infer_estimator.USE_TRUTH:
+                raise ValueError('the inference estimator must not use ground truth')   # main.py:266-267
+        else:
+            self.infer_estimator = self.estimator
+        self.separator = hparams.get_separator(hparams.SEPARATOR_TYPE)(self, 'separator')
+        return self
+
+    def reset(self):
+        """main.py:534-537 initialises variables; here: materialise them with a 1-frame dry run"""
+        F, Cn = hparams.FEATURE_SIZE, hparams.MAX_N_SIGNAL
+        src = torch.zeros((1, Cn, 4, F), dtype=torch.complex64, device=self.device)
+        self.train_forward(src)
+
+    def reset_state(self):
+        """main.py:538-540 -- a no-op by SURVEY.md F7"""
+
+    @staticmethod
+    def _perm_table(Cn, device):
+        return torch.tensor(list(itertools.permutations(range(Cn))), dtype=torch.int64, device=device)
+
+    def _separate_spectra(self, estimator, feats, embed, src_pwr=None):
+        B, T, F, E = embed.shape
+        embed_flat = embed.view(B, T * F, E)
+        attrs = estimator(embed, s_src_pwr=src_pwr, s_mix_pwr=feats['mix_pwr'], s_embed_flat=embed_flat)
+        out = self.separator(feats['mix_pwr'], attrs, embed_flat, s_mixed_signals=feats['mix'],
+                             want=('sep_pwr', 'sep', 'masks'))
+        out['attrs'] = attrs
+        return out
+
+    def train_forward(self, src):
+        """
+        Forward half of the train / valid / debug fetches (main.py:369-397) for complex spectra
+        src [B,C,T,F]: everything `Model.build` wires at main.py:233-337.
+        """
+        src = src.to(self.device)
+        B, Cn, T, F = src.shape
+        feats = K.mix_features(src)                                              # main.py:233-240
+        embed = self.encoder(feats['logmag'])                                    # main.py:243
+        tr = self._separate_spectra(self.estimator, feats, embed, feats['src_pwr'])      # :249-254, :271-284
+        if self.infer_estimator is self.estimator:
+            va = tr                                                              # main.py:259-260
+        else:
+            va = self._separate_spectra(self.infer_estimator, feats, embed)      # main.py:263-278
+        pit = K.pit_mse(src, tr['sep'])                                          # main.py:289
+        perms = self._perm_table(Cn, src.device)
+        sel = perms[pit['perm_idx'].long()]                                      # main.py:293-306
+        bidx = torch.arange(B, device=src.device).unsqueeze(1)
+        output = tr['sep'][bidx, sel]
+        pit_v = K.pit_mse(feats['src_pwr'], va['sep_pwr'])                       # main.py:312
+        # valid SNR (main.py:336): complex error of the re-phased, PIT-aligned magnitudes
+        sel_v = perms[pit_v['perm_idx'].long()]
+        cross_v = K.pit_mse(src, va['sep'])
+        noise = cross_v['cross'].gather(2, sel_v.unsqueeze(-1)).squeeze(-1).mean(1)
+        sig = (pit['cross'].new_zeros(B) + self._signal_power(src))
+        eps = hparams.EPS
+        valid_snr = (4.342944819 * (torch.log(sig + eps) - torch.log(noise + eps))).mean()
+        return dict(embed=embed, attrs=tr['attrs'], attrs_valid=va['attrs'], masks=tr['masks'],
+                    masks_valid=va['masks'], sep_pwr=tr['sep_pwr'], output=output,
+                    train_loss=pit['loss'][0], train_snr=pit['snr'].mean(),
+                    valid_loss=pit_v['loss'][0], valid_snr=valid_snr, infer_signals=va['sep'],
+                    perm_idx=pit['perm_idx'], perm_losses=pit['perm_losses'],
+                    mix=feats['mix'], mix_pwr=feats['mix_pwr'], logmag=feats['logmag'])
+
+    @staticmethod
+    def _signal_power(src):
+        # mean |s|^2 over (C,T,F): reuse the PIT kernel's signal-power output through snr/noise algebra
+        # is not possible for a different permutation, so take it from the cross matrix of (src, 0)
+        z = torch.zeros_like(src)
+        c = K.pit_mse(src, z)['cross']          # cross[b,i,j] = mean |s_i|^2
+        return c[:, :, 0].mean(1)
+
+    def infer(self, mix, logmag=None):
+        """infer fetches (main.py:384-385): complex mixture [B,T,F] -> separated spectra [B,C,T,F]"""
+        B, T, F = mix.shape
+        if logmag is None:
+            feats = K.mix_features(mix.view(B, 1, T, F), want=('mix_pwr', 'logmag'))
+            logmag, mix_pwr = feats['logmag'], feats['mix_pwr']
+        else:
+            mix_pwr = None
+        embed = self.encoder(logmag)
+        embed_flat = embed.view(B, T * F, -1)
+        attrs = self.infer_estimator(embed, s_embed_flat=embed_flat)
+        out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=('sep',))
+        return out['sep']
+
+    def separate(self, wav):
+        """demo path (main.py:660-695): waveforms [B,N] f32 on the device -> [B,C,64*T] f32.
+        STFT (app/utils.py:117-122), infer graph, iSTFT per source (app/utils.py:53-75)."""
+        mix, logmag = K.stft(wav, want_logmag=True)
+        return K.istft(self.infer(mix, logmag=logmag))
+
+    def separate_host(self, wav_host, out_host=None):
+        """The call a user makes: pinned host waveforms in, host waveforms out."""
+        wav = wav_host.to(self.device, non_blocking=True)
+        y = self.separate(wav)
+        if out_host is None:
+            return y.cpu()
+        out_host.copy_(y, non_blocking=True)
+        return out_host

@@ -1,0 +1,210 @@
+"""
+Encoder / Estimator / Separator plugins -- the reference's app/modules.py surface
+(`cls(model, name)`, called like functions, registered with `@hparams.register_*`) on
+CUDA tensors, every computation a call into libdanet_sm100.so (`kernels.py`).
+
+Registered names: encoders `lstm-orig`, `bilstm-orig`; estimators `truth`,
+`truth-threshold`, `truth-weighted`, `anchor`, `kmeans` (new); separators
+`dot-sigmoid-orig`, `dot-softmax-orig`.
+"""
+from math import sqrt
+
+import numpy as np
+
+from . import kernels as K
+from .hparams import hparams
+
+
+class ModelModule(object):
+    """app/modules.py:11-25"""
+    def __init__(self, model, name):
+        if hparams.DEBUG:
+            self.debug_fetches = {}
+        self.name = name
+        self.model = model
+
+    def __call__(self, s_dropout_keep=1.):
+        raise NotImplementedError()
+
+
+class Encoder(ModelModule):
+    """app/modules.py:28-50: log-magnitude [B,T,F] -> embedding [B,T,F,E]"""
+    def __call__(self, s_mixture, s_dropout_keep=1.):
+        raise NotImplementedError()
+
+
+class Estimator(ModelModule):
+    """app/modules.py:53-70: embedding (+ truth) -> attractors [B,C,E]"""
+    USE_TRUTH = True
+
+    def __call__(self, s_embed, **kwargs):
+        raise NotImplementedError()
+
+
+class Separator(ModelModule):
+    """app/modules.py:73-93: (|mix| [B,T,F], attractors [B,C,E], embed_flat [B,TF,E]) -> [B,C,T,F]"""
+    def __call__(self, s_mixed_signals_pwr, s_attractors, s_embed_flat):
+        raise NotImplementedError()
+
+
+def lstm_bias_init(hdim):
+    """app/modules.py:217-221 (and :157-161): [cand 0 | input 1.5 | forget -1 | output 1]"""
+    b = np.zeros([hdim * 4], dtype=np.float32)
+    b[hdim * 1:hdim * 2] = 1.5
+    b[hdim * 2:hdim * 3] = -1.
+    b[hdim * 3:hdim * 4] = 1.
+    return b
+
+
+def _uniform(lo, hi):
+    return lambda rs, shape: rs.uniform(lo, hi, size=shape)
+
+
+def _check_dropout(keep):
+    # the reference never feeds its dropout placeholder into the encoder
+    if keep != 1.:
+        raise NotImplementedError('dropout is dead code in the reference (keep_prob is always 1)')
+
+
+def _lyr_bilstm(name, model, s_input, hdim, w_init, b_init, s_dropout_keep=1.):
+    """app/modules.py:120-137: forward scan, scan of the time-reversed input un-reversed, concat.
+    Both directions run inside ONE recurrent kernel launch."""
+    _check_dropout(s_dropout_keep)
+    return model.lyr_bilstm(name, s_input, hdim, w_init=w_init, b_init=b_init)
+
+
+class _RecurrentEncoder(Encoder):
+    N_LAYERS = 4
+    HDIM = 300
+    INIT_SCALE = .75
+    BIDIR = True
+
+    def _geometry(self):
+        n_layers = getattr(hparams, 'ENCODER_LAYERS', None) or self.N_LAYERS
+        hdim = getattr(hparams, 'ENCODER_HDIM', None) or self.HDIM
+        return n_layers, hdim
+
+    def __call__(self, s_signals, s_dropout_keep=1.):
+        _check_dropout(s_dropout_keep)
+        model = self.model
+        B, T, F = s_signals.shape
+        n_layers, hdim = self._geometry()
+        x = K.center(s_signals)                                    # modules.py:209-210 / :150-151
+        r = self.INIT_SCALE / sqrt(hdim)
+        w_init = _uniform(-r, r)
+        b_init = lambda rs, shape: lstm_bias_init(hdim)
+        for l in range(n_layers):
+            if self.BIDIR:
+                x = _lyr_bilstm('%s/lstm%d' % (self.name, l), model, x, hdim, w_init, b_init, s_dropout_keep)
+            else:
+                x = model.lyr_lstm('%s/lstm%d' % (self.name, l), x, hdim, w_init=w_init, b_init=b_init)
+        x = K.center(x)                                            # modules.py:244-245 / :181-182
+        odim = x.shape[-1]
+        E = hparams.EMBED_SIZE
+        W = model.get_variable('%s/output/W' % self.name, [odim, F * E], _uniform(-1.85, 1.85))
+        v = K.linear(x.view(B * T, odim), W)                       # modules.py:249-255, no bias
+        s_out = v.view(B, T, F, E)
+        if hparams.DEBUG:
+            self.debug_fetches['embed'] = s_out
+        return s_out
+
+
+@hparams.register_encoder('lstm-orig')
+class LstmEncoder(_RecurrentEncoder):
+    """app/modules.py:140-196: 4 x 600 unidirectional"""
+    HDIM = 600
+    INIT_SCALE = 1.15
+    BIDIR = False
+
+
+@hparams.register_encoder('bilstm-orig')
+class BiLstmEncoder(_RecurrentEncoder):
+    """app/modules.py:199-260: 4 x (300 + 300)"""
+
+
+class _TruthEstimator(Estimator):
+    USE_TRUTH = True
+    MODE = 'truth'
+
+    def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
+        if s_src_pwr is None:
+            raise ValueError('estimator "%s" needs the true source magnitudes' % self.MODE)
+        return K.attractor_truth(s_embed, s_src_pwr, s_mix_pwr, self.MODE)
+
+
+@hparams.register_estimator('truth')
+class AverageEstimator(_TruthEstimator):
+    """app/modules.py:382-412"""
+    MODE = 'truth'
+
+
+@hparams.register_estimator('truth-threshold')
+class ThreshouldedAverageEstimator(_TruthEstimator):
+    """app/modules.py:415-450"""
+    MODE = 'truth-threshold'
+
+
+@hparams.register_estimator('truth-weighted')
+class WeightedAverageEstimator(_TruthEstimator):
+    """app/modules.py:453-487"""
+    MODE = 'truth-weighted'
+
+
+def _normal(rs, shape):
+    return rs.standard_normal(size=shape)
+
+
+@hparams.register_estimator('anchor')
+class AnchoredEstimator(Estimator):
+    """app/modules.py:490-545"""
+    USE_TRUTH = False
+
+    def anchors(self):
+        return self.model.get_variable('%s/anchors' % self.name, [hparams.NUM_ANCHOR, hparams.EMBED_SIZE], _normal)
+
+    def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
+        if hparams.DEBUG:
+            out, sets, sims, choice = K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL, True)
+            self.debug_fetches.update(asets=sets, anchors=self.anchors(), subset_choice=choice)
+            return out
+        return K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL)
+
+
+@hparams.register_estimator('kmeans')
+class KMeansEstimator(AnchoredEstimator):
+    """NEW plugin (the reference's README.md:216-217 lists k-means as unimplemented):
+    Lloyd iterations seeded with the anchor estimator's attractors."""
+    USE_TRUTH = False
+    N_ITER = 5
+
+    def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
+        init = K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL)
+        return K.attractor_kmeans(s_embed, init, getattr(hparams, 'KMEANS_ITERS', None) or self.N_ITER)
+
+
+class _DotSeparator(Separator):
+    KIND = None
+
+    def __call__(self, s_mixed_signals_pwr, s_attractors, s_embed_flat, s_mixed_signals=None, want=('sep_pwr',)):
+        """The reference signature returns magnitudes [B,C,T,F].  Extension: passing the complex
+        mixture and `want` also yields the re-phased spectra (main.py:281-284) and the masks from the
+        same pass."""
+        out = K.mask_cmul(s_embed_flat, s_attractors, s_mixed_signals, self.KIND, want=want,
+                          mix_pwr=s_mixed_signals_pwr)
+        if hparams.DEBUG and out.get('masks') is not None:
+            self.debug_fetches['masks'] = out['masks']
+        if tuple(want) == ('sep_pwr',):
+            return out['sep_pwr']
+        return out
+
+
+@hparams.register_separator('dot-sigmoid-orig')
+class DotSeparatorSigmoid(_DotSeparator):
+    """app/modules.py:548-574"""
+    KIND = 'dot-sigmoid-orig'
+
+
+@hparams.register_separator('dot-softmax-orig')
+class DotSeparatorSoftmax(_DotSeparator):
+    """app/modules.py:577-603"""
+    KIND = 'dot-softmax-orig'

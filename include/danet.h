@@ -124,11 +124,13 @@ int danet_attractor_kmeans_fwd(const float* embed, float* centroids,
 /* ---- K4  mask x mixture (+ iSTFT) -------------------------------------------
  * replaces DotSeparatorSoftmax/Sigmoid (app/modules.py:577-603 / :548-574) and the
  * re-phasing at main.py:281-284 (complex(cos(phi)*p, sin(phi)*p) == mask * mix).
- *   embed [B,TF,E], attractors [B,C,E], mix [B,TF] complex ->
+ *   embed [B,TF,E], attractors [B,C,E], mix [B,TF] complex and/or mix_pwr [B,TF] (the
+ *   plugin interface hands the separator magnitudes only; |mix| is computed when
+ *   mix_pwr is NULL; sep_c64 needs mix_c64) ->
  *   sep_pwr (nullable) [B,C,TF]; sep_c64 (nullable) [B,C,TF] complex;
  *   masks (nullable) [B,TF,C].   kind: 0 = softmax over C, 1 = sigmoid. */
 int danet_mask_cmul_fwd(const float* embed, const float* attractors,
-                        const float* mix_c64, float* sep_pwr, float* sep_c64,
+                        const float* mix_c64, const float* mix_pwr, float* sep_pwr, float* sep_c64,
                         float* masks, int B, int C, int TF, int E, int kind,
                         void* stream);
 /* replaces utils.istft (app/utils.py:53-75) incl. its quirks: frames 0..T-5 only,

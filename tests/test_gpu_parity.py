@@ -1,0 +1,348 @@
+"""
+GPU parity tests: every call goes through the C-ABI (libdanet_sm100.so via
+danet_tensorflow_b200.kernels) and is compared with the CPU oracle on the same seeded
+inputs, with the committed golden fixtures (outputs of the reference's own Python), and,
+at BASELINE.json's full sizes, through size-independent properties.
+Tolerance: 1e-3 relative (max-norm) in fp32, as BASELINE.json's north_star states; most
+checks are far tighter and say so.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import danet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def D():
+    import danet_tensorflow_b200 as D
+    D._lib.load()
+    assert D._lib.load().danet_check_device() == 0, D._lib.load().danet_last_error_string()
+    return D
+
+
+@pytest.fixture(scope='module')
+def K(D):
+    return D.kernels
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ---------------------------------------------------------------- K1: STFT / iSTFT
+@pytest.mark.parametrize('n', [256, 257, 320, 777, 4096, 31999, 32000])
+def test_stft_vs_oracle(K, n):
+    rs = np.random.RandomState(n)
+    wav = (rs.standard_normal((3, n)) * 1000.).astype(np.float32)
+    spec, logmag = K.stft(cuda(wav), want_logmag=True)
+    ref = np.stack([O.stft(w) for w in wav])
+    assert spec.shape == ref.shape == (3, O.num_frames(n), 129)
+    assert rel(torch.view_as_real(spec), np.stack([ref.real, ref.imag], -1)) < 2e-6
+    assert rel(logmag, np.log1p(np.abs(ref))) < 2e-6
+
+
+def test_stft_golden(K):
+    a = np.load(os.path.join(GOLDEN, 'audio.npz'))
+    for n in (32000, 31999, 4096, 777, 256):
+        spec = K.stft(cuda(a['wav_%d' % n][None]))[0].cpu().numpy()
+        assert rel(spec, a['stft_%d' % n]) < 5e-6
+    spec = K.stft(cuda(a['wav_sin'][None]))[0].cpu().numpy()
+    assert rel(spec, a['stft_sin']) < 5e-6
+
+
+def test_stft_too_short_raises(K):
+    with pytest.raises(ValueError):
+        K.stft(torch.zeros(1, 100, device='cuda'))
+    with pytest.raises(ValueError):
+        K.stft(torch.zeros(1, 1000))      # host tensor: there is no CPU path
+
+
+def test_stft_empty_batch(K):
+    spec = K.stft(torch.zeros(0, 512, device='cuda'))
+    assert spec.shape == (0, 9, 129)
+
+
+@pytest.mark.parametrize('T', [5, 8, 33, 64, 501])
+def test_istft_vs_oracle(K, T):
+    rs = np.random.RandomState(T)
+    X = (rs.standard_normal((2, T, 129)) + 1j * rs.standard_normal((2, T, 129))).astype(np.complex64)
+    out = K.istft(cuda(X))
+    ref = np.stack([O.istft(x) for x in X])
+    assert out.shape == ref.shape == (2, 64 * T)
+    assert rel(out, ref) < 5e-6
+
+
+def test_istft_golden(K):
+    a = np.load(os.path.join(GOLDEN, 'audio.npz'))
+    assert rel(K.istft(cuda(a['istft_rand_in'][None]))[0], a['istft_rand_out']) < 5e-6
+    for key in ('4096', '777'):
+        X = a['stft_' + key].astype(np.complex64)
+        assert rel(K.istft(cuda(X[None]))[0], a['istft_' + key]) < 5e-6
+
+
+def test_stft_istft_roundtrip_full_size(K):
+    # cfg 2 size: 64 signals of 4 s; y[128+k] * sum(w) == x[k]
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(64, 32000, device='cuda', generator=g) * 1000.
+    y = K.istft(K.stft(x))
+    sw = float(O.fft_window(256, np.float64).sum())
+    n = 32000 - 512
+    err = (y[:, 128 + 64:128 + n] * sw - x[:, 64:n]).abs().max() / x.abs().max()
+    assert float(err) < 1e-5
+
+
+# ---------------------------------------------------------------- features / centring
+def test_mix_features(K):
+    rs = np.random.RandomState(0)
+    src = (rs.standard_normal((3, 2, 17, 129)) + 1j * rs.standard_normal((3, 2, 17, 129))).astype(np.complex64) * 100
+    out = K.mix_features(cuda(src))
+    mix = src.sum(1)
+    assert rel(torch.view_as_real(out['mix']), np.stack([mix.real, mix.imag], -1)) < 1e-6
+    assert rel(out['src_pwr'], np.abs(src)) < 1e-6
+    assert rel(out['mix_pwr'], np.abs(mix)) < 1e-6
+    assert rel(out['logmag'], np.log1p(np.abs(mix.astype(np.complex128)))) < 1e-6
+
+
+def test_center(K):
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((5, 37, 129)).astype(np.float32) + 3.
+    ref = x.astype(np.float64) - x.astype(np.float64).mean(axis=(1, 2), keepdims=True)
+    assert rel(K.center(cuda(x)), ref) < 1e-5
+
+
+# ---------------------------------------------------------------- dense layers
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('M,N,K_,T', [(48, 1200, 129, 8), (1002, 1200, 600, 501), (96, 2580, 600, 0),
+                                      (37, 100, 77, 0), (256, 256, 64, 0)])
+def test_linear(K, backend, M, N, K_, T):
+    rs = np.random.RandomState(M + N)
+    a = rs.standard_normal((M, K_)).astype(np.float32)
+    w = rs.uniform(-1, 1, (K_ + 5, N)).astype(np.float32)
+    b = rs.standard_normal(N).astype(np.float32)
+    out = K.linear(cuda(a), cuda(w), cuda(b), time_major_T=T, backend=backend, k_rows=K_, row_offset=2)
+    ref = a.astype(np.float64) @ w[2:2 + K_].astype(np.float64) + b
+    if T:
+        ref = ref.reshape(M // T, T, N).transpose(1, 0, 2).reshape(M, N)
+    # backend 1 is bf16x3 split precision: ~1e-5 of the output scale
+    assert rel(out, ref) < (2e-6 if backend == 0 else 3e-5)
+
+
+# ---------------------------------------------------------------- recurrent kernel
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('n_dir,B,T,I,H', [(2, 3, 12, 129, 300), (1, 2, 9, 129, 600), (2, 17, 30, 600, 300),
+                                           (2, 32, 40, 600, 300), (2, 1, 25, 129, 300)])
+def test_lstm_seq(K, backend, n_dir, B, T, I, H):
+    rs = np.random.RandomState(B * T)
+    r = .75 / np.sqrt(H)
+    x = rs.standard_normal((B, T, I)).astype(np.float32)
+    Ws = [rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32) for _ in range(n_dir)]
+    Bs = [O.lstm_bias_init(H).astype(np.float32) + 0.1 * rs.standard_normal(4 * H).astype(np.float32)
+          for _ in range(n_dir)]
+    xg = cuda(x).reshape(B * T, I)
+    pre = torch.empty(n_dir, T, B, 4 * H, device='cuda')
+    Wg = [cuda(w) for w in Ws]
+    for d in range(n_dir):
+        K.linear(xg, Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
+    out, cell = K.lstm_seq(pre, Wg, I, T, B, H, backend=backend, keep_cell=True)
+    xt = torch.from_numpy(x).double()
+    refs = [O.lstm_layer(xt, torch.from_numpy(Ws[0]).double(), torch.from_numpy(Bs[0]).double())]
+    if n_dir == 2:
+        refs.append(torch.flip(O.lstm_layer(torch.flip(xt, [1]), torch.from_numpy(Ws[1]).double(),
+                                            torch.from_numpy(Bs[1]).double()), [1]))
+    ref = torch.cat(refs, -1)
+    assert rel(out, ref) < (1e-5 if backend == 0 else 1e-4)
+    assert cell.shape == (n_dir, T, B, H) and bool(torch.isfinite(cell).all())
+
+
+# ---------------------------------------------------------------- K3: attractors
+def _embed_case(rs, B, C, T, E):
+    V = rs.standard_normal((B, T, 129, E)).astype(np.float32) * 3.
+    src_pwr = np.abs(rs.standard_normal((B, C, T, 129))).astype(np.float32) * 10.
+    mix_pwr = np.abs(rs.standard_normal((B, T, 129))).astype(np.float32) * 10.
+    return V, src_pwr, mix_pwr
+
+
+@pytest.mark.parametrize('mode', ['truth', 'truth-threshold', 'truth-weighted'])
+@pytest.mark.parametrize('B,C,T,E', [(3, 2, 9, 20), (2, 3, 130, 40), (1, 2, 1, 4)])
+def test_attractor_truth(K, mode, B, C, T, E):
+    rs = np.random.RandomState(T)
+    V, sp, mp = _embed_case(rs, B, C, T, E)
+    fn = {'truth': O.estimator_truth, 'truth-threshold': O.estimator_truth_threshold,
+          'truth-weighted': O.estimator_truth_weighted}[mode]
+    ref = fn(torch.from_numpy(V).double(), torch.from_numpy(sp).double(), torch.from_numpy(mp).double())
+    out = K.attractor_truth(cuda(V), cuda(sp), cuda(mp), mode)
+    assert rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize('B,C,T,E', [(3, 2, 9, 20), (2, 3, 70, 40), (2, 3, 6, 12), (1, 2, 501, 20)])
+def test_attractor_anchor(K, B, C, T, E):
+    rs = np.random.RandomState(T + C)
+    V, _, _ = _embed_case(rs, B, C, T, E)
+    anchors = rs.standard_normal((6, E)).astype(np.float32)
+    ref, sets, sim, choice = O.estimator_anchor(torch.from_numpy(V).double(), torch.from_numpy(anchors).double(),
+                                                C, return_all=True)
+    out, gsets, gsim, gchoice = K.attractor_anchor(cuda(V), cuda(anchors), C, return_all=True)
+    assert rel(gsets, sets) < 5e-5
+    assert rel(gsim, sim) < 5e-5
+    # discrete choice must agree wherever the oracle's margin is not a numerical tie
+    s = np.sort(sim.numpy(), axis=1)
+    clear = (s[:, 1] - s[:, 0]) > 1e-4 * np.abs(s[:, 0])
+    assert np.array_equal(gchoice.cpu().numpy()[clear], choice.numpy()[clear])
+    if clear.all():
+        assert rel(out, ref) < 5e-5
+
+
+def test_attractor_kmeans(K):
+    # new plugin, no reference twin ("parity unpinned"): checked against the NumPy-style restatement
+    rs = np.random.RandomState(5)
+    B, C, T, E = 2, 3, 40, 20
+    cen0 = rs.standard_normal((B, C, E)).astype(np.float32) * 4
+    lab = rs.randint(0, C, (B, T, 129))
+    V = (cen0[np.arange(B)[:, None, None], lab] + rs.standard_normal((B, T, 129, E))).astype(np.float32)
+    init = (cen0 + rs.standard_normal((B, C, E))).astype(np.float32)
+    ref = O.estimator_kmeans(torch.from_numpy(V).double(), C, n_iter=5, init=torch.from_numpy(init).double())
+    out = K.attractor_kmeans(cuda(V), cuda(init), 5)
+    assert rel(out, ref) < 2e-5
+
+
+# ---------------------------------------------------------------- K4: mask x mixture
+@pytest.mark.parametrize('kind', ['dot-softmax-orig', 'dot-sigmoid-orig'])
+@pytest.mark.parametrize('B,C,T,E', [(3, 2, 9, 20), (2, 3, 33, 40), (2, 3, 5, 12)])
+def test_mask_cmul(K, kind, B, C, T, E):
+    rs = np.random.RandomState(T)
+    V = rs.standard_normal((B, T, 129, E)).astype(np.float32)
+    A = rs.standard_normal((B, C, E)).astype(np.float32)
+    mix = (rs.standard_normal((B, T, 129)) + 1j * rs.standard_normal((B, T, 129))).astype(np.complex64) * 50
+    mixt = torch.from_numpy(mix).to(torch.complex128)
+    ref_pwr, ref_m = O.separator(mixt.abs(), torch.from_numpy(A).double(),
+                                 torch.from_numpy(V).double().reshape(B, -1, E), kind, return_mask=True)
+    ph = torch.atan2(mixt.imag, mixt.real).unsqueeze(1)
+    ref_sig = torch.complex(torch.cos(ph) * ref_pwr, torch.sin(ph) * ref_pwr)     # main.py:281-284
+    out = K.mask_cmul(cuda(V).view(B, -1, E), cuda(A), cuda(mix), kind)
+    assert rel(out['masks'], ref_m) < 1e-5
+    assert rel(out['sep_pwr'], ref_pwr) < 1e-5
+    assert rel(torch.view_as_real(out['sep']), torch.view_as_real(ref_sig)) < 1e-5
+    # the plugin signature: magnitudes only
+    out2 = K.mask_cmul(cuda(V).view(B, -1, E), cuda(A), None, kind, mix_pwr=cuda(np.abs(mix)))
+    assert rel(out2['sep_pwr'], ref_pwr) < 1e-5 and out2['sep'] is None
+
+
+# ---------------------------------------------------------------- K5: PIT-MSE + SNR
+@pytest.mark.parametrize('cplx', [True, False])
+@pytest.mark.parametrize('B,C,T', [(4, 2, 7), (3, 3, 40), (2, 1, 5)])
+def test_pit_mse(K, cplx, B, C, T):
+    rs = np.random.RandomState(B + C)
+    x = rs.standard_normal((B, C, T, 129)) + 1j * rs.standard_normal((B, C, T, 129))
+    perm = np.stack([rs.permutation(C) for _ in range(B)])
+    y = x[np.arange(B)[:, None], perm] + 0.3 * (rs.standard_normal(x.shape) + 1j * rs.standard_normal(x.shape))
+    if not cplx:
+        x, y = np.abs(x), np.abs(y)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    loss, perms, idx, L = O.pit_mse_loss(xt, yt)
+    snr = O.batch_snr(xt, O.pit_reorder(yt, perms, idx))
+    dt = np.complex64 if cplx else np.float32
+    out = K.pit_mse(cuda(x.astype(dt)), cuda(y.astype(dt)))
+    assert rel(out['perm_losses'], L) < 1e-5
+    assert np.array_equal(out['perm_idx'].cpu().numpy(), idx.numpy())
+    assert abs(float(out['loss'][0]) - float(loss)) < 1e-5 * abs(float(loss))
+    assert rel(out['snr'], snr) < 1e-4
+
+
+def test_pit_golden(K):
+    d = np.load(os.path.join(GOLDEN, 'ops.npz'))
+    out = K.pit_mse(cuda(d['pit_x'].astype(np.complex64)), cuda(d['pit_y'].astype(np.complex64)))
+    assert abs(float(out['loss'][0]) - float(d['pit_c_loss'])) < 1e-5 * abs(float(d['pit_c_loss']))
+    assert np.array_equal(out['perm_idx'].cpu().numpy(), d['pit_c_idx'])
+    assert rel(out['snr'], d['snr_c']) < 1e-4
+
+
+# ---------------------------------------------------------------- whole model vs the reference's outputs
+MODEL_FILES = sorted(p for p in glob.glob(os.path.join(GOLDEN, 'model_*.npz')) if 'toy' not in os.path.basename(p)
+                     or 'truth' in os.path.basename(p))
+
+
+def _load_case(path):
+    d = np.load(path)
+    meta = json.loads(str(d['meta']))
+    over = meta['over']
+    est = [v[0].split('/')[1] for v in meta['var_order'] if v[0].endswith('anchors:0')]
+    P = O.reference_init(meta['seed'], encoder=over.get('ENCODER_TYPE', 'toy'),
+                         embed=over.get('EMBED_SIZE', 20), estimators=tuple(est))
+    return d, meta, over, P
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('path', MODEL_FILES, ids=[os.path.basename(p)[6:-4] for p in MODEL_FILES])
+def test_model_forward_golden(D, path, backend):
+    d, meta, over, P = _load_case(path)
+    hp = D.Hyperparameter()
+    hp.load({k: v for k, v in over.items() if k not in ('FLOATX', 'DEBUG')})
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(hp.__dict__)
+    D.hparams.digest()
+    D.kernels.DEFAULT_BACKEND = backend
+    model = D.Model('golden').build()
+    model.load_params(P)
+    out = model.train_forward(cuda(d['src'].astype(np.complex64)))
+    assert rel(out['embed'], d['dbg_embed']) < TOL
+    assert rel(out['attrs'], d['dbg_attrs']) < TOL
+    assert rel(out['masks_valid'], d['dbg_masks']) < TOL
+    assert rel(torch.view_as_real(out['output']), np.stack([d['dbg_output'].real, d['dbg_output'].imag], -1)) < TOL
+    assert rel(torch.view_as_real(out['infer_signals']),
+               np.stack([d['infer_signals'].real, d['infer_signals'].imag], -1)) < TOL
+    for k in ('train_loss', 'train_snr', 'valid_loss', 'valid_snr'):
+        assert abs(float(out[k]) - float(d[k])) <= TOL * max(1., abs(float(d[k]))), k
+
+
+def test_model_init_matches_reference_stream(D):
+    # product initialisers draw the same RandomState stream as the fixtures' weights
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(D.Hyperparameter().__dict__)
+    D.hparams.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor'))
+    D.hparams.digest()
+    model = D.Model('init', seed=1337).build()
+    model.reset()
+    P = O.reference_init(1337, estimators=('train_estimator',), dtype=torch.float32)
+    assert set(P) == set(model.params)
+    for k, v in P.items():
+        assert np.array_equal(model.params[k].cpu().numpy(), v.numpy()), k
+    assert model.parameter_count() == 9067200 + 120
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+def test_separate_waveforms(D, backend):
+    """wav -> wav (demo path) against the oracle on a 1 s utterance pair"""
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(D.Hyperparameter().__dict__)
+    D.hparams.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                        SEPARATOR_TYPE='dot-softmax-orig'))
+    D.hparams.digest()
+    D.kernels.DEFAULT_BACKEND = backend
+    rs = np.random.RandomState(2)
+    wav = (rs.standard_normal((2, 8000)) * 1000.).astype(np.float32)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float32)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav, P, dtype=torch.float32)
+    model = D.Model('sep').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    out = model.separate(cuda(wav))
+    assert rel(out, ref_wav) < TOL

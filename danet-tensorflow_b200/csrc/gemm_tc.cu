@@ -1,0 +1,259 @@
+// Dense layers on the 5th-generation tensor cores (backend 1 of danet_linear_fwd):
+//   C[M,N] = A[M,K] * W[K,N] (+ bias)   -- app/ops.py:72-89 (lyr_linear)
+// fp32 parity (1e-3 end to end after 2004 recurrent steps) rules out plain bf16/tf32 operands
+// (measured 5e-3 / 6e-4 on the embedding), so operands are split x = hi + lo into two bf16 and
+// three products hi*hi + hi*lo + lo*hi accumulate in fp32 in TMEM ("bf16x3", ~1e-5).
+//   1. split kernels write A -> [hi;lo] bf16 [2M, Kp] and W^T -> [hi;lo] bf16 [2N, Kp]
+//      (K-major, K zero-padded to a multiple of 64) into the caller's workspace;
+//   2. gemm kernel: 128x128 output tile per CTA, TMA (SWIZZLE_128B) -> 3-stage smem ring ->
+//      tcgen05.mma kind::f16 M128 N128 K16, accumulator in 128 TMEM columns, epilogue warps
+//      tcgen05.ld -> + bias -> global (optionally [B,T] -> [T,B] row remap).
+#include <cuda.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace danet {
+
+using namespace tc;
+
+constexpr int kTM = 128, kTN = 128, kTK = 64;
+constexpr int kStages = 3;
+constexpr int kTileBytes = kTM * kTK * 2;                 // 16 KB: one bf16 operand tile
+constexpr int kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, B_hi, B_lo
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+static inline int pad_k(int K) { return (K + kTK - 1) / kTK * kTK; }
+
+// ---- operand split --------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int Kp,
+                  __nv_bfloat16* __restrict__ out) {
+  // out[0..M) = hi rows, out[M..2M) = lo rows, each Kp wide
+  const long long total = (long long)M * (Kp / 2);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int m = (int)(i / (Kp / 2)), k = (int)(i % (Kp / 2)) * 2;
+    const float x0 = k < K ? __ldg(A + (size_t)m * lda + k) : 0.f;
+    const float x1 = k + 1 < K ? __ldg(A + (size_t)m * lda + k + 1) : 0.f;
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(x0, h0, l0);
+    split_bf16(x1, h1, l1);
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)m * Kp + k) = __nv_bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(M + m) * Kp + k) = __nv_bfloat162(l0, l1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N, int Kp,
+                       __nv_bfloat16* __restrict__ out) {
+  // W [K,N] row-major -> out[n][k] hi rows [0,N), lo rows [N,2N); 32x32 tiles through smem
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < K && n < N) ? __ldg(W + (size_t)k * ldw + n) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < N && k < Kp) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[tx][r], h, l);
+      out[(size_t)n * Kp + k] = h;
+      out[(size_t)(N + n) * Kp + k] = l;
+    }
+  }
+}
+
+// ---- tcgen05 GEMM ------------------------------------------------------------------------
+struct GemmParams {
+  const float* bias;
+  float* C;
+  int M, N, n_kblocks, T, nb;   // T > 0: logical row b*T+t is stored at row t*nb+b
+};
+
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  const int nkb = p.n_kblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* st = smem + s * kStageBytes;
+        mbar_arrive_expect_tx(full_bar + s, kStageBytes);
+        tma_load_2d(st, &map_a, full_bar + s, kb * kTK, m0);                          // A hi
+        tma_load_2d(st + kTileBytes, &map_a, full_bar + s, kb * kTK, p.M + m0);       // A lo
+        tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + s, kb * kTK, n0);         // W^T hi
+        tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + s, kb * kTK, p.N + n0);   // W^T lo
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(kTM, kTN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_hi = umma_desc_k_sw128(base), a_lo = umma_desc_k_sw128(base + kTileBytes);
+        const uint64_t b_hi = umma_desc_k_sw128(base + 2 * kTileBytes), b_lo = umma_desc_k_sw128(base + 3 * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTK / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K16 step inside the swizzle row
+          umma_bf16(tmem_acc, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          umma_bf16(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
+          umma_bf16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1);
+        }
+        umma_commit(empty_bar + s);                    // smem slot reusable once these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full_bar); // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp q owns TMEM lanes 32q..32q+31 = output rows m0+32q+lane =====
+    const int q = warp - 4;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + 32 * q + lane;
+    const bool row_ok = row < p.M;
+    const size_t orow = p.T > 0 ? (size_t)(row % p.T) * p.nb + row / p.T : (size_t)row;
+    float* crow = p.C + orow * p.N;
+    const bool vec = (p.N & 3) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kTN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;                       // warp-uniform
+      float v[32];
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v);
+      if (row_ok) {
+        if (vec && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + n0 + c0 + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.N) crow[n] = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_acc, kTN);
+}
+
+// ---- host -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, Kp] row-major, box = 64 (K) x box_rows, 128-byte swizzle
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, long long rows, int Kp, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  DANET_REQUIRE(enc, DANET_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kTK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DANET_REQUIRE(r == CUDA_SUCCESS, DANET_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DANET_OK;
+}
+
+size_t linear_tc_workspace_bytes(int M, int N, int K) {
+  const size_t Kp = pad_k(K);
+  return ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024 + (size_t)2 * N * Kp * 2 + 1024;
+}
+
+int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, float* C,
+                  int M, int N, int K, int time_major_T, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+  DANET_REQUIRE(workspace, DANET_E_ARG, "linear: tcgen05 backend needs a workspace");
+  DANET_REQUIRE(workspace_bytes >= linear_tc_workspace_bytes(M, N, K), DANET_E_WORKSPACE,
+                "linear: workspace %zu < %zu", workspace_bytes, linear_tc_workspace_bytes(M, N, K));
+  DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "linear: C and bias must be 16-byte aligned");
+  const int Kp = pad_k(K);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* A2 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* W2 = reinterpret_cast<__nv_bfloat16*>(ws + ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024);
+  {
+    const long long total = (long long)M * (Kp / 2);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(A, lda, M, K, Kp, A2);
+    DANET_LAUNCH_CHECK();
+    dim3 g(Kp / 32, (N + 31) / 32);
+    split_transpose_kernel<<<g, 256, 0, stream>>>(W, ldw, K, N, Kp, W2);
+    DANET_LAUNCH_CHECK();
+  }
+  CUtensorMap map_a, map_b;
+  int rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
+  if (rc) return rc;
+  rc = make_tensor_map_bf16(&map_b, W2, 2ll * N, Kp, kTN);
+  if (rc) return rc;
+  GemmParams p;
+  p.bias = bias; p.C = C; p.M = M; p.N = N; p.n_kblocks = Kp / kTK;
+  p.T = time_major_T; p.nb = time_major_T > 0 ? M / time_major_T : 0;
+  DANET_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+  dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
+  DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "linear: M %d too large", M);
+  gemm_bf16x3_kernel<<<grid, 256, kGemmSmem, stream>>>(map_a, map_b, p);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+}  // namespace danet

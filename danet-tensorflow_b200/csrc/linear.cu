@@ -7,7 +7,9 @@
 namespace danet {
 
 int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias,
-                  float* C, int M, int N, int K, int time_major_T, cudaStream_t stream);
+                  float* C, int M, int N, int K, int time_major_T, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+size_t linear_tc_workspace_bytes(int M, int N, int K);
 
 constexpr int kBM = 128, kBN = 128, kBK = 16;
 
@@ -74,9 +76,14 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
 
 using namespace danet;
 
+extern "C" size_t danet_linear_workspace_bytes(int M, int N, int K, int backend) {
+  if (backend != 1 || M < 1 || N < 1 || K < 1) return 256;
+  return linear_tc_workspace_bytes(M, N, K);
+}
+
 extern "C" int danet_linear_fwd(const float* A, long long lda, const float* W, long long ldw,
                                 const float* bias, float* C, int M, int N, int K, int time_major_T,
-                                int backend, void* stream) {
+                                void* workspace, size_t workspace_bytes, int backend, void* stream) {
   DANET_REQUIRE(A && W && C, DANET_E_ARG, "linear: null pointer");
   DANET_REQUIRE(M >= 0 && N >= 1 && K >= 1 && lda >= K && ldw >= N, DANET_E_SHAPE,
                 "linear: M %d N %d K %d lda %lld ldw %lld", M, N, K, lda, ldw);
@@ -85,7 +92,8 @@ extern "C" int danet_linear_fwd(const float* A, long long lda, const float* W, l
   DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "linear: backend %d", backend);
   if (M == 0) return DANET_OK;
   if (backend == 1)
-    return linear_tc_fwd(A, lda, W, ldw, bias, C, M, N, K, time_major_T, as_stream(stream));
+    return linear_tc_fwd(A, lda, W, ldw, bias, C, M, N, K, time_major_T, workspace, workspace_bytes,
+                         as_stream(stream));
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
   DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "linear: M %d too large", M);
   sgemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, lda, W, ldw, bias, C, M, N, K, time_major_T);

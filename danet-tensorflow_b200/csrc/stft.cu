@@ -180,8 +180,9 @@ extern "C" int danet_stft_num_frames(int n_samples) {
 
 extern "C" int danet_stft_fwd(const float* wav, int n_sig, int n_samples, float* spec_c64,
                               float* logmag, void* stream) {
-  DANET_REQUIRE(wav && spec_c64, DANET_E_ARG, "stft: null pointer");
   DANET_REQUIRE(n_sig >= 0, DANET_E_SHAPE, "stft: n_sig %d", n_sig);
+  if (n_sig == 0 && n_samples >= kFft) return DANET_OK;
+  DANET_REQUIRE(wav && spec_c64, DANET_E_ARG, "stft: null pointer");
   DANET_REQUIRE(n_samples >= kFft, DANET_E_SHAPE,
                 "stft: window is longer than input signal (%d < 256)", n_samples);
   DANET_REQUIRE(aligned8(spec_c64), DANET_E_ALIGN, "stft: spec must be 8-byte aligned");
@@ -197,8 +198,9 @@ extern "C" int danet_stft_fwd(const float* wav, int n_sig, int n_samples, float*
 }
 
 extern "C" int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* stream) {
-  DANET_REQUIRE(spec_c64 && wav, DANET_E_ARG, "istft: null pointer");
   DANET_REQUIRE(n_sig >= 0 && T >= 1, DANET_E_SHAPE, "istft: n_sig %d T %d", n_sig, T);
+  if (n_sig == 0) return DANET_OK;
+  DANET_REQUIRE(spec_c64 && wav, DANET_E_ARG, "istft: null pointer");
   DANET_REQUIRE(aligned8(spec_c64), DANET_E_ALIGN, "istft: spec must be 8-byte aligned");
   if (n_sig == 0) return DANET_OK;
   DANET_REQUIRE(n_sig <= 65535, DANET_E_SHAPE, "istft: n_sig %d > 65535", n_sig);

@@ -1,10 +1,6 @@
 // Temporary: tcgen05 back ends not built yet.
 #include "common.cuh"
 namespace danet {
-int linear_tc_fwd(const float*, long long, const float*, long long, const float*, float*, int, int, int, int, cudaStream_t) {
-  set_error("linear: tcgen05 backend not built");
-  return DANET_E_ARG;
-}
 int lstm_tc_fwd(const float*, const float* const*, long long, float*, float*, int, int, int, int, void*, size_t, cudaStream_t) {
   set_error("lstm_seq: tcgen05 backend not built");
   return DANET_E_ARG;

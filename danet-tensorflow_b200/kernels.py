@@ -140,9 +140,11 @@ def linear(a, w, bias=None, time_major_T=0, backend=None, k_rows=None, row_offse
         raise ValueError('linear: out must be a contiguous float32 [%d,%d]' % (M, N))
     wp = C.c_void_p(w.data_ptr() + row_offset * N * 4)
     be = DEFAULT_BACKEND if backend is None else backend
-    _lib.check(_lib.load().danet_linear_fwd(_p(a), K, wp, N, _p(bias), _p(out), M, N, K, int(time_major_T),
-                                            be, _stream()), 'linear')
-    _count()
+    lib = _lib.load()
+    ws = _ws(lib.danet_linear_workspace_bytes(M, N, K, be), a.device)
+    _lib.check(lib.danet_linear_fwd(_p(a), K, wp, N, _p(bias), _p(out), M, N, K, int(time_major_T),
+                                    _p(ws), ws.numel(), be, _stream()), 'linear')
+    _count(3 if be == 1 else 1)
     return out
 
 

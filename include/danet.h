@@ -73,10 +73,14 @@ int danet_center_fwd(const float* x, int B, long long n_per, float* y,
  * C[M,N] = A[M,K] (row stride lda) * W[K,N] (row stride ldw) (+ bias[N]).
  * If time_major_T > 0 the logical row r = b*T + t of A is written to output row
  * t*(M/T) + b (the [T,B,N] layout the recurrent kernel consumes).
- * backend: 0 = exact fp32 SIMT, 1 = tcgen05 bf16x3 (fp32-grade split precision). */
+ * backend: 0 = exact fp32 SIMT (no workspace), 1 = tcgen05 bf16x3: operands split
+ * x = hi + lo into bf16 pairs staged in the workspace, three tensor-core products
+ * hi*hi + hi*lo + lo*hi accumulated in fp32 (error ~1e-5 of the output scale). */
+size_t danet_linear_workspace_bytes(int M, int N, int K, int backend);
 int danet_linear_fwd(const float* A, long long lda, const float* W, long long ldw,
                      const float* bias, float* C, int M, int N, int K,
-                     int time_major_T, int backend, void* stream);
+                     int time_major_T, void* workspace, size_t workspace_bytes,
+                     int backend, void* stream);
 
 /* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------
  * replaces Model.lyr_lstm (main.py:76-132: tf.scan from zero state) over

@@ -17,6 +17,8 @@ FFT_STRIDE = 64
 # 0 = exact fp32 SIMT kernels, 1 = tcgen05 (bf16x3 split operands, fp32 accumulate)
 DEFAULT_BACKEND = int(os.environ.get('DANET_BACKEND', '1'))
 
+TC_LSTM_MAX_H = 320
+
 # launch counter: bench.py reports how many of OUR kernels ran inside the timed region
 launches = 0
 
@@ -171,7 +173,11 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False):
     lib = _lib.load()
     nws = lib.danet_lstm_seq_workspace_bytes(n_dir, B, H)
     ws = _ws(nws, pre.device)
-    be = DEFAULT_BACKEND if backend is None else backend
+    if backend is None:
+        # the tcgen05 cluster kernel keeps Wh in one cluster's shared memory: H <= 320
+        be = DEFAULT_BACKEND if H <= TC_LSTM_MAX_H else 0
+    else:
+        be = backend
     _lib.check(lib.danet_lstm_seq_fwd(_p(pre), ptrs, 4 * H, _p(out), _p(cell), n_dir, T, B, H, _p(ws),
                                       ws.numel(), be, _stream()), 'lstm_seq')
     _count()

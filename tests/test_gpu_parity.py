@@ -163,6 +163,10 @@ def test_lstm_seq(K, backend, n_dir, B, T, I, H):
     xg = cuda(x).reshape(B * T, I)
     pre = torch.empty(n_dir, T, B, 4 * H, device='cuda')
     Wg = [cuda(w) for w in Ws]
+    if backend == 1 and H > K.TC_LSTM_MAX_H:
+        with pytest.raises(ValueError):      # documented limit of the cluster-resident kernel
+            K.lstm_seq(pre, Wg, I, T, B, H, backend=1)
+        return
     for d in range(n_dir):
         K.linear(xg, Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
     out, cell = K.lstm_seq(pre, Wg, I, T, B, H, backend=backend, keep_cell=True)

@@ -105,7 +105,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
+    if (elect_one_sync()) {   // ===== TMA producer =====
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -119,7 +119,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
+    if (elect_one_sync()) {   // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_bf16(kTM, kTN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;

@@ -3,17 +3,21 @@
 // thread-block-cluster kernel.
 //
 // One cluster = one direction x 16 utterances.  CTA r of the cluster owns hidden units
-// [32r, 32r+32) and keeps the 128 gate rows (4 gates x 32 units, row m = 4*unit + gate) of
-// Wh^T resident in shared memory for the whole sequence as bf16 hi/lo pairs (160 KB at
-// H = 300, K padded to 320).  Per step the CTA issues  D[128 gate rows, 16 utterances] =
-// Wh^T[128, K] * h_{t-1}^T[K, 16]  as 60 tcgen05.mma (M128 N16 K16; bf16x3: hi*hi + hi*lo +
-// lo*hi, fp32 accumulate in TMEM), the epilogue warps read TMEM, add the hoisted input
+// [32r, 32r+32).  Its 128 gate rows (4 gates x 32 units, row m = 4*unit + gate) of Wh^T stay
+// resident in TENSOR MEMORY for the whole sequence as packed bf16 hi/lo pairs (2 x K/2 = 320
+// of the 512 TMEM columns at H = 300, K padded to 320), so the A operand never touches the
+// shared-memory port (a shared-memory resident A costs 4 KB of reads per MMA: measured 65
+// cycles per MMA, 3900 cycles per step).  Per step the CTA issues
+//   D[128 gate rows, 16 utterances] = Wh^T[128, K] * h_{t-1}^T[K, 16]
+// as 60 tcgen05.mma (A from TMEM, B from smem, M128 N16 K16; bf16x3: hi*hi + hi*lo + lo*hi,
+// fp32 accumulate in TMEM).  The epilogue warps read the accumulator, add the hoisted input
 // projection, apply  c = sig(i)*g + sig(f)*c ; h = sig(o)*tanh(c)  (candidate WITHOUT tanh),
 // write h_t to the output, and broadcast their 32-unit slice of h_t (bf16 hi/lo, already in
 // the UMMA K-major SWIZZLE_64B layout: K-block r of the B operand IS CTA r's slice) into every
 // CTA's shared memory with one cp.async.bulk (DSMEM) per peer, completing on the peer's
 // mbarrier.  No global-memory round trip and no cluster-wide barrier sits on the T-step
 // critical path.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -24,12 +28,13 @@ using namespace tc;
 constexpr int kUnits = 32;            // hidden units per CTA
 constexpr int kRows = 128;            // gate rows per CTA = UMMA M
 constexpr int kNB = 16;               // utterances per cluster = UMMA N
-constexpr int kMaxCta = 10;           // cluster size limit from shared memory (H <= 320)
-constexpr int kATile = kRows * 64;    // bytes of one [128 x 32] bf16 K-block of A (SW64)
+constexpr int kMaxCta = 12;           // cluster size limit (TMEM: 32 + 2*16*ncta <= 512 columns)
 constexpr int kHTile = kNB * 64;      // bytes of one [16 x 32] bf16 K-block of h (SW64) = 1 KB
 constexpr int kXchLd = 17;
 constexpr int kEpiThreads = 128;
 constexpr int kThreads = 160;         // 4 epilogue warps + 1 MMA warp
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 32;          // accumulator: columns [0,16) of the first 32
 
 struct LstmTcParams {
   const float* pre;        // [n_dir][T][B][4H]
@@ -38,7 +43,14 @@ struct LstmTcParams {
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
   int n_dir, T, B, H;
+  long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
 };
+
+constexpr int kProfSlots = 16;
+#define DANET_PROF(slot)                                                                   \
+  do {                                                                                     \
+    if (prof_on) p.prof[(size_t)s * kProfSlots + (slot)] = clock64();                      \
+  } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -71,9 +83,15 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
   const int r = row & 7;
   return (uint32_t)((row >> 3) * 512 + r * 64 + ((((kk >> 3) ^ (r >> 1)) & 3) << 4) + (kk & 7) * 2);
 }
-
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// sigma(x) and tanh(x) from ex2.approx / rcp.approx: ~3e-7 absolute error, far inside the bf16x3
+// error of the recurrent product, and 4-5x shorter than expf/tanhf on the step's critical path
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -86,78 +104,95 @@ lstm_tc_kernel(const LstmTcParams p) {
   const int H = p.H, T = p.T, B = p.B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // shared memory carve-up (all tile bases 1024-byte aligned)
-  uint8_t* sA = smem;                                          // [hi|lo][ncta][kATile]
-  uint8_t* sH = sA + 2 * ncta * kATile;                        // [2 buf][ncta][hi|lo][kHTile]
+  // shared memory carve-up (tile bases 1024-byte aligned)
+  uint8_t* sH = smem;                                          // [2 buf][ncta][hi|lo][kHTile]
   uint8_t* sStage = sH + 2 * ncta * 2 * kHTile;                // [2][hi|lo][kHTile]
   float* sXch = reinterpret_cast<float*>(sStage + 2 * 2 * kHTile);   // [128][17]
-  uint64_t* h_full = reinterpret_cast<uint64_t*>(sXch + kRows * kXchLd + 2);   // 8-byte aligned: 128*17+2 floats
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(sXch + kRows * kXchLd + 2);   // 128*17+2 floats: 8-byte aligned
   uint64_t* acc_full = h_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int unit0 = rank * kUnits;
   const int b0 = bt * kNB;
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                       (tid == 0 || warp == 4);
 
-  // ---- one-time: Wh^T slice -> bf16 hi/lo, UMMA K-major SW64 layout ----
-  {
-    const float* Wg = p.Wh[dir];
-    const int Kp = ncta * 32;
-    for (int i = tid; i < 4 * Kp * kUnits; i += kThreads) {
-      const int u = i % kUnits, g = (i / kUnits) & 3, k = i / (4 * kUnits);
-      const int unit = unit0 + u;
-      float w = 0.f;
-      if (unit < H && k < H) w = __ldg(Wg + (size_t)k * p.ldw + g * H + unit);
-      __nv_bfloat16 hi, lo;
-      split_bf16(w, hi, lo);
-      const int m = 4 * u + g;
-      const uint32_t off = (uint32_t)(k >> 5) * kATile + sw64_offset(m, k & 31);
-      *reinterpret_cast<__nv_bfloat16*>(sA + off) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(sA + ncta * kATile + off) = lo;
-    }
-  }
   if (tid == 0) {
     mbar_init(h_full + 0, 1);
     mbar_init(h_full + 1, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 32);
-  fence_proxy_async_smem();          // generic-proxy stores of sA -> visible to tcgen05.mma
+  if (warp == 4) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc = tmem_base;
+  const uint32_t tmem_a_hi = tmem_base + kAccCols;              // ncta*16 columns
+  const uint32_t tmem_a_lo = tmem_a_hi + (uint32_t)ncta * 16;
+
+  // ---- one-time: this CTA's rows of Wh^T -> packed bf16 hi/lo in TMEM (lane = gate row) ----
+  if (warp < 4) {
+    const int m = tid, u = m >> 2, g = m & 3, unit = unit0 + u;
+    const float* wcol = p.Wh[dir] + (size_t)g * H + unit;      // W[k][g*H + unit], stride ldw over k
+    const bool unit_ok = unit < H;
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    for (int k0 = 0; k0 < ncta * 32; k0 += 16) {
+      float w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = (unit_ok && k0 + i < H) ? __ldg(wcol + (size_t)(k0 + i) * p.ldw) : 0.f;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(w[2 * i], h0, l0);
+        split_bf16(w[2 * i + 1], h1, l1);
+        hi[i] = pack_bf16(h0, h1);
+        lo[i] = pack_bf16(l0, l1);
+      }
+      tmem_st_32x8(tmem_a_hi + lane_sel + (k0 >> 1), hi);
+      tmem_st_32x8(tmem_a_lo + lane_sel + (k0 >> 1), lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   cluster_sync();                    // every CTA's barriers are initialised before any peer signals them
 
   const uint32_t h_bytes = (uint32_t)ncta * 2 * kHTile;   // one full h_t (hi+lo, all K-blocks)
 
   if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       if (T >= 2) mbar_arrive_expect_tx(h_full + 0, h_bytes);     // h_0 lands in buffer 0
       if (T >= 3) mbar_arrive_expect_tx(h_full + 1, h_bytes);     // h_1 lands in buffer 1
       constexpr uint32_t idesc = umma_idesc_bf16(kRows, kNB);
-      const uint32_t a_base = smem_u32(sA);
       for (int s = 1; s < T; ++s) {
         const int buf = (s - 1) & 1;
+        DANET_PROF(0);
         mbar_wait(h_full + buf, ((s - 1) >> 1) & 1);              // h_{s-1} complete in sH[buf]
+        DANET_PROF(1);
         if (s + 1 <= T - 2) mbar_arrive_expect_tx(h_full + buf, h_bytes);   // re-arm for h_{s+1}
         tc_fence_after();
-        const uint32_t h_base = smem_u32(sH + (size_t)buf * ncta * 2 * kHTile);
+        const uint64_t b0d = umma_desc_k_sw64(smem_u32(sH + (size_t)buf * ncta * 2 * kHTile));
+#pragma unroll 2
         for (int j = 0; j < ncta; ++j) {
-          const uint64_t a_hi = umma_desc_k_sw64(a_base + j * kATile);
-          const uint64_t a_lo = umma_desc_k_sw64(a_base + (ncta + j) * kATile);
-          const uint64_t b_hi = umma_desc_k_sw64(h_base + j * 2 * kHTile);
-          const uint64_t b_lo = umma_desc_k_sw64(h_base + j * 2 * kHTile + kHTile);
+          // K-block j: h slice of CTA j at +j*2 KB (hi) / +1 KB (lo); A columns j*16 (+8 per K16 step)
+          const uint64_t b_hi = b0d + (uint64_t)((j * 2 * kHTile) >> 4);
+          const uint64_t b_lo = b_hi + (uint64_t)(kHTile >> 4);
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);               // 32 bytes per K16 step
-            umma_bf16(tmem_acc, a_hi + adv, b_hi + adv, idesc, (j | k) != 0);
-            umma_bf16(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_bf16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1);
+            const uint32_t ac = (uint32_t)(j * 16 + k * 8);
+            const uint64_t adv = (uint64_t)(k * 2);               // 32 bytes per K16 step inside the 64 B row
+            umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_hi + adv, idesc, (j | k) != 0);
+            umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_lo + adv, idesc, 1);
+            umma_bf16_ts(tmem_acc, tmem_a_lo + ac, b_hi + adv, idesc, 1);
           }
         }
         umma_commit(acc_full);
+        DANET_PROF(2);
       }
     }
   } else {
@@ -183,27 +218,27 @@ lstm_tc_kernel(const LstmTcParams p) {
     const int outw = p.n_dir * H;
     float* xw = sXch + m * kXchLd;
     const uint32_t stage_off = sw64_offset(bl, ub);      // 8 contiguous bytes: units ub..ub+3 of utterance bl
+    // this lane's broadcast target (lanes 0..ncta-1 of warp 0 each feed one peer)
+    const int peer = (rank + lane) % ncta;
+    const uint32_t peer_dst0 = mapa(smem_u32(sH + (size_t)rank * 2 * kHTile), peer);
+    const uint32_t peer_bar0 = mapa(smem_u32(h_full), peer);
 
     for (int s = 0; s < T; ++s) {
       const int to = dir ? T - 1 - s : s;
       float a[4][4];                                     // [unit][gate]
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        a[0][g] = (&pre_next[g].x)[0]; a[1][g] = (&pre_next[g].x)[1];
-        a[2][g] = (&pre_next[g].x)[2]; a[3][g] = (&pre_next[g].x)[3];
-      }
+      a[0][0] = pre_next[0].x; a[1][0] = pre_next[0].y; a[2][0] = pre_next[0].z; a[3][0] = pre_next[0].w;
+      a[0][1] = pre_next[1].x; a[1][1] = pre_next[1].y; a[2][1] = pre_next[1].z; a[3][1] = pre_next[1].w;
+      a[0][2] = pre_next[2].x; a[1][2] = pre_next[2].y; a[2][2] = pre_next[2].z; a[3][2] = pre_next[2].w;
+      a[0][3] = pre_next[3].x; a[1][3] = pre_next[3].y; a[2][3] = pre_next[3].z; a[3][3] = pre_next[3].w;
       load_pre(s + 1);
+      DANET_PROF(3);
       if (s > 0) {
         mbar_wait(acc_full, (s - 1) & 1);
+        DANET_PROF(4);
         tc_fence_after();
         float v[16];
-        {
-          float lo8[8], hi8[8];
-          tmem_ld_32x8(tmem_acc + ((uint32_t)(32 * warp) << 16), lo8);
-          tmem_ld_32x8(tmem_acc + ((uint32_t)(32 * warp) << 16) + 8, hi8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { v[i] = lo8[i]; v[8 + i] = hi8[i]; }
-        }
+        tmem_ld_32x16(tmem_acc + ((uint32_t)(32 * warp) << 16), v);
+        DANET_PROF(5);
         tc_fence_before();
         __syncwarp();                                    // previous step's reads of sXch are done
 #pragma unroll
@@ -214,15 +249,17 @@ lstm_tc_kernel(const LstmTcParams p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) a[uu][g] += sXch[(4 * (ub + uu) + g) * kXchLd + bl];
       }
+      DANET_PROF(6);
       float h[4];
 #pragma unroll
       for (int uu = 0; uu < 4; ++uu) {
         const float gg = a[uu][0];
-        const float ig = sigmoidf_(a[uu][1]), fg = sigmoidf_(a[uu][2]), og = sigmoidf_(a[uu][3]);
+        const float ig = fast_sigmoid(a[uu][1]), fg = fast_sigmoid(a[uu][2]), og = fast_sigmoid(a[uu][3]);
         c[uu] = ig * gg + fg * c[uu];
-        h[uu] = og * tanhf(c[uu]);
+        h[uu] = og * fast_tanh(c[uu]);
       }
       if (!valid) { h[0] = h[1] = h[2] = h[3] = 0.f; }
+      DANET_PROF(7);
       if (s < T - 1) {
         // my 4 units of h_s as bf16 hi/lo into the staging K-block (already UMMA layout)
         __nv_bfloat16 hi[4], lo[4];
@@ -234,15 +271,12 @@ lstm_tc_kernel(const LstmTcParams p) {
             make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (tid == 0) {
-          const uint32_t src = smem_u32(st);
-          const uint32_t dst_local = smem_u32(sH + ((size_t)(s & 1) * ncta + rank) * 2 * kHTile);
-          const uint32_t bar_local = smem_u32(h_full + (s & 1));
-          for (int d = 0; d < ncta; ++d) {
-            const int peer = (rank + d) % ncta;          // stagger the destinations
-            dsmem_bulk_copy(mapa(dst_local, peer), src, 2 * kHTile, mapa(bar_local, peer));
-          }
+        DANET_PROF(8);
+        if (warp == 0 && lane < ncta) {
+          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * 2 * kHTile;
+          dsmem_bulk_copy(peer_dst0 + boff, smem_u32(st), 2 * kHTile, peer_bar0 + (uint32_t)(s & 1) * 8);
         }
+        DANET_PROF(9);
       }
       if (valid) {
         *reinterpret_cast<float4*>(p.out + ((size_t)b * T + to) * outw + dir * H + unit) =
@@ -257,12 +291,11 @@ lstm_tc_kernel(const LstmTcParams p) {
   tc_fence_before();
   __syncthreads();
   cluster_sync();
-  if (warp == 4) tmem_dealloc(tmem_acc, 32);
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 static size_t lstm_tc_smem_bytes(int ncta) {
-  return (size_t)2 * ncta * kATile + (size_t)2 * ncta * 2 * kHTile + 2 * 2 * kHTile +
-         (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
+  return (size_t)2 * ncta * 2 * kHTile + 2 * 2 * kHTile + (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
 }
 
 size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
@@ -271,15 +304,18 @@ bool lstm_tc_supported(int H) { return H % 4 == 0 && (H + kUnits - 1) / kUnits <
 
 int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
                 int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
-                "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's shared memory and needs "
+                "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
                 "H <= %d (got %d); use backend 0", kMaxCta * kUnits, H);
   DANET_REQUIRE(aligned16(pre) && aligned16(out) && (!cell_seq || aligned16(cell_seq)), DANET_E_ALIGN,
                 "lstm_seq: pre/out/cell_seq must be 16-byte aligned");
+  long long* prof = nullptr;
+  if (getenv("DANET_LSTM_PROFILE") && workspace && workspace_bytes >= (size_t)T * kProfSlots * sizeof(long long)) {
+    prof = reinterpret_cast<long long*>(workspace);
+    DANET_CUDA(cudaMemsetAsync(prof, 0, (size_t)T * kProfSlots * sizeof(long long), stream));
+  }
   const size_t smem = lstm_tc_smem_bytes(ncta);
-  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: %zu B of shared memory needed", smem);
   DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ncta > 8) DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   LstmTcParams p;
@@ -287,7 +323,7 @@ int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, fl
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
   p.ldw = ldw; p.out = out; p.cell_seq = cell_seq;
-  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ncta, (B + kNB - 1) / kNB, n_dir);
   cfg.blockDim = dim3(kThreads);

@@ -27,9 +27,12 @@ using namespace tc;
 
 constexpr int kUnits = 32;            // hidden units per CTA
 constexpr int kRows = 128;            // gate rows per CTA = UMMA M
-constexpr int kNB = 16;               // utterances per cluster = UMMA N
+constexpr int kUmmaN = 16;            // UMMA N (minimum for M = 128); NB = 8 or 16 columns carry utterances
 constexpr int kMaxCta = 12;           // cluster size limit (TMEM: 32 + 2*16*ncta <= 512 columns)
-constexpr int kHTile = kNB * 64;      // bytes of one [16 x 32] bf16 K-block of h (SW64) = 1 KB
+// One K-block (32 units) of the B operand h^T, 2 KB: [atom0: hi 512 B | lo 512 B][atom1: hi | lo], an atom
+// being 8 utterance rows x 64 B in SWIZZLE_64B; hi and lo descriptors differ by 512 B and both use SBO = 1024.
+// With NB = 8 only atom0 ever changes, so a CTA ships 1 KB per peer per step instead of 2 KB.
+constexpr int kHBlock = 2048;
 constexpr int kXchLd = 17;
 constexpr int kEpiThreads = 128;
 constexpr int kThreads = 160;         // 4 epilogue warps + 1 MMA warp
@@ -73,15 +76,15 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t s
       ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
       : "memory");
 }
-// K-major SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms of 512 bytes (SBO = 512)
+// K-major SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms of 512 bytes, atoms 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (4ull << 61);
 }
-// byte offset of element (row, kk) inside a SW64 K-block tile (kk in [0,32))
+// byte offset of the hi element (row, kk) inside a K-block (kk in [0,32)); lo is 512 bytes further
 __device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
   const int r = row & 7;
-  return (uint32_t)((row >> 3) * 512 + r * 64 + ((((kk >> 3) ^ (r >> 1)) & 3) << 4) + (kk & 7) * 2);
+  return (uint32_t)((row >> 3) * 1024 + r * 64 + ((((kk >> 3) ^ (r >> 1)) & 3) << 4) + (kk & 7) * 2);
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
@@ -94,8 +97,11 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_kernel(const LstmTcParams p) {
+  constexpr int UPT = NB / 4;                      // hidden units per epilogue thread (4 or 2)
+  constexpr uint32_t kSendBytes = NB * 128;        // per peer per step: NB rows x (64 B hi + 64 B lo)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int ncta = gridDim.x;                      // cluster size = K-blocks
@@ -105,24 +111,29 @@ lstm_tc_kernel(const LstmTcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // shared memory carve-up (tile bases 1024-byte aligned)
-  uint8_t* sH = smem;                                          // [2 buf][ncta][hi|lo][kHTile]
-  uint8_t* sStage = sH + 2 * ncta * 2 * kHTile;                // [2][hi|lo][kHTile]
-  float* sXch = reinterpret_cast<float*>(sStage + 2 * 2 * kHTile);   // [128][17]
-  uint64_t* h_full = reinterpret_cast<uint64_t*>(sXch + kRows * kXchLd + 2);   // 128*17+2 floats: 8-byte aligned
+  uint8_t* sH = smem;                                          // [2 buf][ncta][kHBlock]
+  uint8_t* sStage = sH + 2 * ncta * kHBlock;                   // [2][kHBlock]
+  float* sXch = reinterpret_cast<float*>(sStage + 2 * kHBlock);      // [128][17]
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(sXch + kRows * kXchLd + 2);   // [2 buf], 8-byte aligned
   uint64_t* acc_full = h_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int unit0 = rank * kUnits;
-  const int b0 = bt * kNB;
+  const int b0 = bt * NB;
   const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
                        (tid == 0 || warp == 4);
 
   if (tid == 0) {
-    mbar_init(h_full + 0, 1);
-    mbar_init(h_full + 1, 1);
+    // one arrival (+ expect_tx) per source CTA and phase, posted remotely by the sender itself
+    mbar_init(h_full + 0, ncta);
+    mbar_init(h_full + 1, ncta);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
+  // rows NB..15 of every K-block (and all of h_{-1}) are zero for the whole run
+  for (int i = tid; i < (2 * ncta + 2) * kHBlock / 16; i += kThreads)
+    reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   if (warp == 4) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -161,31 +172,25 @@ lstm_tc_kernel(const LstmTcParams p) {
   tc_fence_after();
   cluster_sync();                    // every CTA's barriers are initialised before any peer signals them
 
-  const uint32_t h_bytes = (uint32_t)ncta * 2 * kHTile;   // one full h_t (hi+lo, all K-blocks)
-
   if (warp == 4) {
     // ================= MMA issuer =================
     if (elect_one_sync()) {
-      if (T >= 2) mbar_arrive_expect_tx(h_full + 0, h_bytes);     // h_0 lands in buffer 0
-      if (T >= 3) mbar_arrive_expect_tx(h_full + 1, h_bytes);     // h_1 lands in buffer 1
-      constexpr uint32_t idesc = umma_idesc_bf16(kRows, kNB);
+      constexpr uint32_t idesc = umma_idesc_bf16(kRows, kUmmaN);
       for (int s = 1; s < T; ++s) {
         const int buf = (s - 1) & 1;
+        const uint64_t b0d = umma_desc_k_sw64(smem_u32(sH + (size_t)buf * ncta * kHBlock));
         DANET_PROF(0);
-        mbar_wait(h_full + buf, ((s - 1) >> 1) & 1);              // h_{s-1} complete in sH[buf]
+        mbar_wait(h_full + buf, ((s - 1) >> 1) & 1);              // every slice of h_{s-1} is in sH[buf]
         DANET_PROF(1);
-        if (s + 1 <= T - 2) mbar_arrive_expect_tx(h_full + buf, h_bytes);   // re-arm for h_{s+1}
         tc_fence_after();
-        const uint64_t b0d = umma_desc_k_sw64(smem_u32(sH + (size_t)buf * ncta * 2 * kHTile));
 #pragma unroll 2
         for (int j = 0; j < ncta; ++j) {
-          // K-block j: h slice of CTA j at +j*2 KB (hi) / +1 KB (lo); A columns j*16 (+8 per K16 step)
-          const uint64_t b_hi = b0d + (uint64_t)((j * 2 * kHTile) >> 4);
-          const uint64_t b_lo = b_hi + (uint64_t)(kHTile >> 4);
+          const uint64_t b_hi = b0d + (uint64_t)((j * kHBlock) >> 4);
+          const uint64_t b_lo = b_hi + (uint64_t)(512 >> 4);
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const uint32_t ac = (uint32_t)(j * 16 + k * 8);
-            const uint64_t adv = (uint64_t)(k * 2);               // 32 bytes per K16 step inside the 64 B row
+            const uint32_t ac = (uint32_t)(j * 16 + k * 8);        // A columns of this K16 step
+            const uint64_t adv = (uint64_t)(k * 2);                 // 32 bytes inside the 64 B row
             umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_hi + adv, idesc, (j | k) != 0);
             umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_lo + adv, idesc, 1);
             umma_bf16_ts(tmem_acc, tmem_a_lo + ac, b_hi + adv, idesc, 1);
@@ -198,92 +203,125 @@ lstm_tc_kernel(const LstmTcParams p) {
   } else {
     // ================= epilogue warps: TMEM lane m = 32*warp + lane = 4*unit + gate =================
     const int m = tid;
-    // cell-update ownership: utterance bl = lane % 16, units ub..ub+3 (ub = 8*warp + 4*(lane/16))
-    const int bl = lane & 15, ub = 8 * warp + 4 * (lane >> 4);
+    // cell-update ownership: utterance bl = lane % NB, units ub..ub+UPT-1 of this warp's 8 units
+    const int bl = lane % NB, ub = 8 * warp + UPT * (lane / NB);
     const int b = b0 + bl, unit = unit0 + ub;
-    const bool valid = b < B && unit < H;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 pre_next[4];
+    const bool valid = b < B && unit < H;            // H % 4 == 0 and ub % UPT == 0: all-or-nothing
+    float c[UPT];
+#pragma unroll
+    for (int uu = 0; uu < UPT; ++uu) c[uu] = 0.f;
+    float pre_next[4][UPT];
     auto load_pre = [&](int s) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pre_next[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int uu = 0; uu < UPT; ++uu) pre_next[g][uu] = 0.f;
       if (valid && s < T) {
         const int to = dir ? T - 1 - s : s;
         const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pre_next[g] = __ldg(reinterpret_cast<const float4*>(q + g * H));
+        for (int g = 0; g < 4; ++g) {
+          if (UPT == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(q + g * H));
+            pre_next[g][0] = v.x; pre_next[g][1] = v.y; pre_next[g][UPT - 2] = v.z; pre_next[g][UPT - 1] = v.w;
+          } else {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(q + g * H));
+            pre_next[g][0] = v.x; pre_next[g][1] = v.y;
+          }
+        }
       }
     };
     load_pre(0);
     const int outw = p.n_dir * H;
     float* xw = sXch + m * kXchLd;
-    const uint32_t stage_off = sw64_offset(bl, ub);      // 8 contiguous bytes: units ub..ub+3 of utterance bl
-    // this lane's broadcast target (lanes 0..ncta-1 of warp 0 each feed one peer)
-    const int peer = (rank + lane) % ncta;
-    const uint32_t peer_dst0 = mapa(smem_u32(sH + (size_t)rank * 2 * kHTile), peer);
-    const uint32_t peer_bar0 = mapa(smem_u32(h_full), peer);
+    const uint32_t stage_off = sw64_offset(bl, ub);      // UPT contiguous bf16: units ub.. of utterance bl
+    // broadcast: warp w ships this CTA's slice to peers rank+w, rank+w+4, rank+w+8 (one elected lane each)
+    uint32_t peer_dst[3], peer_bar[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int peer = (rank + warp + 4 * i) % ncta;
+      peer_dst[i] = mapa(smem_u32(sH + (size_t)rank * kHBlock), peer);
+      peer_bar[i] = mapa(smem_u32(h_full), peer);
+    }
 
     for (int s = 0; s < T; ++s) {
       const int to = dir ? T - 1 - s : s;
-      float a[4][4];                                     // [unit][gate]
-      a[0][0] = pre_next[0].x; a[1][0] = pre_next[0].y; a[2][0] = pre_next[0].z; a[3][0] = pre_next[0].w;
-      a[0][1] = pre_next[1].x; a[1][1] = pre_next[1].y; a[2][1] = pre_next[1].z; a[3][1] = pre_next[1].w;
-      a[0][2] = pre_next[2].x; a[1][2] = pre_next[2].y; a[2][2] = pre_next[2].z; a[3][2] = pre_next[2].w;
-      a[0][3] = pre_next[3].x; a[1][3] = pre_next[3].y; a[2][3] = pre_next[3].z; a[3][3] = pre_next[3].w;
+      float a[UPT][4];                                   // [unit][gate]
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) a[uu][g] = pre_next[g][uu];
       load_pre(s + 1);
       DANET_PROF(3);
       if (s > 0) {
         mbar_wait(acc_full, (s - 1) & 1);
         DANET_PROF(4);
         tc_fence_after();
-        float v[16];
-        tmem_ld_32x16(tmem_acc + ((uint32_t)(32 * warp) << 16), v);
+        float v[NB];
+        if (NB == 16) tmem_ld_32x16(tmem_acc + ((uint32_t)(32 * warp) << 16), *reinterpret_cast<float(*)[16]>(v));
+        else tmem_ld_32x8(tmem_acc + ((uint32_t)(32 * warp) << 16), *reinterpret_cast<float(*)[8]>(v));
         DANET_PROF(5);
         tc_fence_before();
         __syncwarp();                                    // previous step's reads of sXch are done
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xw[j] = v[j];
+        for (int j = 0; j < NB; ++j) xw[j] = v[j];
         __syncwarp();
 #pragma unroll
-        for (int uu = 0; uu < 4; ++uu)
+        for (int uu = 0; uu < UPT; ++uu)
 #pragma unroll
           for (int g = 0; g < 4; ++g) a[uu][g] += sXch[(4 * (ub + uu) + g) * kXchLd + bl];
       }
       DANET_PROF(6);
-      float h[4];
+      float h[UPT];
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
+      for (int uu = 0; uu < UPT; ++uu) {
         const float gg = a[uu][0];
         const float ig = fast_sigmoid(a[uu][1]), fg = fast_sigmoid(a[uu][2]), og = fast_sigmoid(a[uu][3]);
         c[uu] = ig * gg + fg * c[uu];
-        h[uu] = og * fast_tanh(c[uu]);
+        h[uu] = valid ? og * fast_tanh(c[uu]) : 0.f;
       }
-      if (!valid) { h[0] = h[1] = h[2] = h[3] = 0.f; }
       DANET_PROF(7);
       if (s < T - 1) {
-        // my 4 units of h_s as bf16 hi/lo into the staging K-block (already UMMA layout)
-        __nv_bfloat16 hi[4], lo[4];
+        // my units of h_s as bf16 hi/lo into the staging K-block (already UMMA layout)
+        __nv_bfloat16 hi[UPT], lo[UPT];
 #pragma unroll
-        for (int uu = 0; uu < 4; ++uu) split_bf16(h[uu], hi[uu], lo[uu]);
-        uint8_t* st = sStage + (s & 1) * 2 * kHTile;
-        *reinterpret_cast<uint2*>(st + stage_off) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-        *reinterpret_cast<uint2*>(st + kHTile + stage_off) =
-            make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+        for (int uu = 0; uu < UPT; ++uu) split_bf16(h[uu], hi[uu], lo[uu]);
+        uint8_t* st = sStage + (s & 1) * kHBlock;
+        if (UPT == 4) {
+          *reinterpret_cast<uint2*>(st + stage_off) =
+              make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[UPT - 2], hi[UPT - 1]));
+          *reinterpret_cast<uint2*>(st + 512 + stage_off) =
+              make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[UPT - 2], lo[UPT - 1]));
+        } else {
+          *reinterpret_cast<uint32_t*>(st + stage_off) = pack_bf16(hi[0], hi[1]);
+          *reinterpret_cast<uint32_t*>(st + 512 + stage_off) = pack_bf16(lo[0], lo[1]);
+        }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         DANET_PROF(8);
-        if (warp == 0 && lane < ncta) {
-          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * 2 * kHTile;
-          dsmem_bulk_copy(peer_dst0 + boff, smem_u32(st), 2 * kHTile, peer_bar0 + (uint32_t)(s & 1) * 8);
+        {
+          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kHBlock;
+          const uint32_t bar_off = (uint32_t)(s & 1) * 8;
+          const uint32_t src = smem_u32(st);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (warp + 4 * i < ncta && elect_one_sync()) {
+              mbar_arrive_expect_tx_cluster(peer_bar[i] + bar_off, kSendBytes);
+              dsmem_bulk_copy(peer_dst[i] + boff, src, kSendBytes, peer_bar[i] + bar_off);
+            }
         }
         DANET_PROF(9);
       }
       if (valid) {
-        *reinterpret_cast<float4*>(p.out + ((size_t)b * T + to) * outw + dir * H + unit) =
-            make_float4(h[0], h[1], h[2], h[3]);
-        if (p.cell_seq)
-          *reinterpret_cast<float4*>(p.cell_seq + (((size_t)dir * T + to) * B + b) * H + unit) =
-              make_float4(c[0], c[1], c[2], c[3]);
+        float* o = p.out + ((size_t)b * T + to) * outw + dir * H + unit;
+        float* cs = p.cell_seq ? p.cell_seq + (((size_t)dir * T + to) * B + b) * H + unit : nullptr;
+        if (UPT == 4) {
+          *reinterpret_cast<float4*>(o) = make_float4(h[0], h[1], h[UPT - 2], h[UPT - 1]);
+          if (cs) *reinterpret_cast<float4*>(cs) = make_float4(c[0], c[1], c[UPT - 2], c[UPT - 1]);
+        } else {
+          *reinterpret_cast<float2*>(o) = make_float2(h[0], h[1]);
+          if (cs) *reinterpret_cast<float2*>(cs) = make_float2(c[0], c[1]);
+        }
       }
     }
   }
@@ -295,7 +333,29 @@ lstm_tc_kernel(const LstmTcParams p) {
 }
 
 static size_t lstm_tc_smem_bytes(int ncta) {
-  return (size_t)2 * ncta * 2 * kHTile + 2 * 2 * kHTile + (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
+  return (size_t)(2 * ncta + 2) * kHBlock + (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
+}
+
+template <int NB>
+static int launch_lstm_tc(const LstmTcParams& p, int ncta, cudaStream_t stream) {
+  const size_t smem = lstm_tc_smem_bytes(ncta);
+  DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ncta > 8)
+    DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ncta, (p.B + NB - 1) / NB, p.n_dir);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DANET_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_kernel<NB>, p));
+  return DANET_OK;
 }
 
 size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
@@ -315,29 +375,40 @@ int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, fl
     prof = reinterpret_cast<long long*>(workspace);
     DANET_CUDA(cudaMemsetAsync(prof, 0, (size_t)T * kProfSlots * sizeof(long long), stream));
   }
-  const size_t smem = lstm_tc_smem_bytes(ncta);
-  DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ncta > 8) DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   LstmTcParams p;
   p.pre = pre;
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
   p.ldw = ldw; p.out = out; p.cell_seq = cell_seq;
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ncta, (B + kNB - 1) / kNB, n_dir);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = ncta;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DANET_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_kernel, p));
-  return DANET_OK;
+  // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
+  // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
+  const int clusters8 = n_dir * ((B + 7) / 8);
+  int resident = 0;
+  {
+    const size_t smem = lstm_tc_smem_bytes(ncta);
+    DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ncta > 8)
+      DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta, clusters8, 1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&resident, lstm_tc_kernel<8>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      resident = num_sms() / (ncta + 2);
+    }
+  }
+  const char* force = getenv("DANET_LSTM_NB");
+  const int nb = force ? atoi(force) : (clusters8 <= resident ? 8 : 16);
+  return nb == 8 ? launch_lstm_tc<8>(p, ncta, stream) : launch_lstm_tc<16>(p, ncta, stream);
 }
 
 }  // namespace danet

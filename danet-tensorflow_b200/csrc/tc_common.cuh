@@ -49,6 +49,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
+// one arrival + expected bytes on a barrier of ANOTHER CTA of the cluster (the sender announces its
+// own bulk copy, so the receiver never has to re-arm)
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t remote_bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote_bar_addr),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -77,39 +77,49 @@ def cpu_reference_rate(wav, threads, repeats=1):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons sampled through NVML every 20 ms during the timed region
+    (same quantities as the nvidia-smi line of B200_PROFILING.md, without a process spawn per sample)"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
+        if nv is None:
+            return
         while not self._halt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
-                self.rows.append([c.strip() for c in out.stdout.strip().split(',')])
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, 'nvmlDeviceGetCurrentClocksEventReasons') else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), int(rs)))
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
-        self.join(timeout=6)
-        sm, mx, reasons = [], 0., set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.join(timeout=2)
+        nv = self.nv
+        if nv is None or not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'samples': 0}
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        return {'sm_mhz': float(np.median([c for c, _ in self.rows])), 'sm_max_mhz': self.max_sm,
+                'reasons': reasons, 'samples': len(self.rows)}
 
 
 def run_reference(args, rank):
@@ -231,11 +241,7 @@ def main():
             evs.append((e0, e1))
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return D.shard.max_over_ranks(ms, dev)
 
     for _ in range(max(args.warmup, 3)):
         model.separate(wav_dev)

@@ -5,7 +5,7 @@ kernels behind a C-ABI (include/danet.h), under the Encoder / Estimator / Separa
 surface of khaotik/DaNet-Tensorflow.  Import name: `danet_tensorflow_b200` (see the loader
 module of that name at the repository root; the directory name carries a hyphen).
 """
-from . import _lib, build, kernels
+from . import _lib, build, kernels, shard
 from .hparams import hparams, Hyperparameter
 from . import modules
 from .modules import Encoder, Estimator, Separator, ModelModule

@@ -34,6 +34,162 @@ struct AttParams {
   int subsets[20 * kAttMaxC];   // anchor index table [P][C]
 };
 
+// phase 1 for one time-frequency bin: the R row weights Wt[tf][:]
+template <int MODE>
+__device__ __forceinline__ void row_weights(const AttParams& p, int b, long long tf, bool in_range,
+                                            const float* __restrict__ v, const float* __restrict__ sAux,
+                                            float* __restrict__ w) {
+  const int E = p.E, C = p.C, R = p.R;
+  const long long TF = p.TF;
+  if (!in_range) {
+    for (int r = 0; r < R; ++r) w[r] = 0.f;
+  } else if (MODE == MODE_TRUTH) {
+    const float* sp = p.src_pwr + (size_t)b * C * TF + tf;
+    int k = 0;
+    float best = __ldg(sp);
+    for (int c = 1; c < C; ++c) {          // first maximum on ties (modules.py:396)
+      const float x = __ldg(sp + (size_t)c * TF);
+      if (x > best) { best = x; k = c; }
+    }
+    float wt = 1.f;
+    if (p.truth_mode == 1) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf) > 5.f ? 1.f : 0.f;
+    if (p.truth_mode == 2) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf);
+    for (int c = 0; c < C; ++c) w[c] = c == k ? wt : 0.f;
+  } else if (MODE == MODE_ANCHOR) {
+    float logit[kMaxAnchor];
+#pragma unroll
+    for (int a = 0; a < kMaxAnchor; ++a) logit[a] = 0.f;
+    for (int e = 0; e < E; e += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(v + e);
+#pragma unroll
+      for (int a = 0; a < kMaxAnchor; ++a)
+        if (a < p.n_anchor) {
+          const float4 an = *reinterpret_cast<const float4*>(sAux + a * E + e);
+          logit[a] = fmaf(x.x, an.x, logit[a]);
+          logit[a] = fmaf(x.y, an.y, logit[a]);
+          logit[a] = fmaf(x.z, an.z, logit[a]);
+          logit[a] = fmaf(x.w, an.w, logit[a]);
+        }
+    }
+    for (int s = 0; s < p.n_sub; ++s) {     // eq.6: softmax over the subset's anchors
+      float l[kAttMaxC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kAttMaxC; ++c)
+        if (c < C) {
+          const int a = p.subsets[s * kAttMaxC + c];
+          float lv = logit[0];
+#pragma unroll
+          for (int q = 1; q < kMaxAnchor; ++q) lv = a == q ? logit[q] : lv;
+          l[c] = lv;
+          mx = fmaxf(mx, lv);
+        }
+      float den = 0.f;
+#pragma unroll
+      for (int c = 0; c < kAttMaxC; ++c)
+        if (c < C) { l[c] = expf(l[c] - mx); den += l[c]; }
+      const float inv = 1.f / den;
+#pragma unroll
+      for (int c = 0; c < kAttMaxC; ++c)
+        if (c < C) w[s * C + c] = l[c] * inv;
+    }
+  } else {   // k-means: nearest centroid, first minimum on ties
+    int k = 0;
+    float best = INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float d = 0.f;
+      for (int e = 0; e < E; ++e) {
+        const float t = v[e] - sAux[c * E + e];
+        d = fmaf(t, t, d);
+      }
+      if (d < best) { best = d; k = c; }
+    }
+    for (int c = 0; c < C; ++c) w[c] = c == k ? 1.f : 0.f;
+  }
+}
+
+// Fast path, E = 4*NQ known at compile time: 256 bins per tile, phase 1 one bin per thread, phase 2
+// thread (row r, group g) keeps the whole row accumulator (E sums + the weight sum) in registers and
+// walks the bins g, g+G, ...: 1 weight load + NQ broadcast float4 loads per 4*NQ+1 FMAs.
+constexpr int kTileRT = 256;
+
+template <int MODE, int NQ>
+__global__ void __launch_bounds__(256)
+attractor_partial_rt_kernel(const AttParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int E = 4 * NQ;
+  const int C = p.C, R = p.R, ldv = p.ldv;
+  float* sV = smem;                                  // [kTileRT][ldv]
+  float* sW = sV + kTileRT * ldv;                    // [kTileRT][R]
+  float* sAux = sW + kTileRT * R;                    // anchors / centroids (16-byte aligned: R*256 floats)
+  const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x;
+  const long long TF = p.TF;
+  const float* Vb = p.embed + (size_t)b * TF * E;
+  const int n_aux = MODE == MODE_ANCHOR ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
+  for (int i = tid; i < n_aux; i += 256)
+    sAux[i] = MODE == MODE_KMEANS ? p.aux[(size_t)b * C * E + i] : p.aux[i];
+
+  const int G = 256 / R;                             // bin-interleaved groups per row (R <= 256)
+  const int r = tid % R, g = tid / R;
+  const bool active = g < G;
+  float acc[E];
+  float den = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+
+  const long long n_tiles = (TF + kTileRT - 1) / kTileRT;
+  const long long tiles_per = (n_tiles + kParts - 1) / kParts;
+  const long long t_lo = part * tiles_per;
+  const long long t_hi = t_lo + tiles_per < n_tiles ? t_lo + tiles_per : n_tiles;
+  for (long long tile = t_lo; tile < t_hi; ++tile) {
+    const long long tf0 = tile * kTileRT;
+    const int n_here = (int)(TF - tf0 < kTileRT ? TF - tf0 : kTileRT);
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(Vb + (size_t)tf0 * E);
+      for (int i = tid; i < n_here * NQ; i += 256) {
+        const float4 x = __ldg(src + i);
+        *reinterpret_cast<float4*>(sV + (i / NQ) * ldv + 4 * (i % NQ)) = x;
+      }
+    }
+    __syncthreads();
+    row_weights<MODE>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * R);
+    __syncthreads();
+    if (active) {
+      for (int tfl = g; tfl < n_here; tfl += G) {
+        const float wv = sW[tfl * R + r];
+        const float* vr = sV + tfl * ldv;
+        den += wv;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(vr + 4 * q);
+          acc[4 * q + 0] = fmaf(wv, x.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(wv, x.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(wv, x.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(wv, x.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  // fixed-order reduction of the G groups through shared memory
+  __syncthreads();
+  constexpr int LD = E + 4;                          // partial row layout: E sums, weight sum, 3 zeros
+  float* red = smem;                                 // [G][R][LD]
+  if (active) {
+    float* o = red + ((size_t)g * R + r) * LD;
+#pragma unroll
+    for (int e = 0; e < E; ++e) o[e] = acc[e];
+    o[E] = den; o[E + 1] = 0.f; o[E + 2] = 0.f; o[E + 3] = 0.f;
+  }
+  __syncthreads();
+  float* dst = p.part + ((size_t)b * kParts + part) * R * LD;
+  for (int i = tid; i < R * LD; i += 256) {
+    float sum = red[i];
+    for (int gg = 1; gg < G; ++gg) sum += red[(size_t)gg * R * LD + i];
+    dst[i] = sum;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 attractor_partial_kernel(const AttParams p) {
@@ -78,77 +234,8 @@ attractor_partial_kernel(const AttParams p) {
       }
     }
     __syncthreads();
-    if (tid < kTile) {   // phase 1: row weights of bin tf0 + tid
-      float* w = sW + tid * R;
-      if (tid >= n_here) {
-        for (int r = 0; r < R; ++r) w[r] = 0.f;
-      } else if (MODE == MODE_TRUTH) {
-        const long long tf = tf0 + tid;
-        const float* sp = p.src_pwr + (size_t)b * C * TF + tf;
-        int k = 0;
-        float best = __ldg(sp);
-        for (int c = 1; c < C; ++c) {          // first maximum on ties (modules.py:396)
-          const float v = __ldg(sp + (size_t)c * TF);
-          if (v > best) { best = v; k = c; }
-        }
-        float wt = 1.f;
-        if (p.truth_mode == 1) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf) > 5.f ? 1.f : 0.f;
-        if (p.truth_mode == 2) wt = __ldg(p.mix_pwr + (size_t)b * TF + tf);
-        for (int c = 0; c < C; ++c) w[c] = c == k ? wt : 0.f;
-      } else if (MODE == MODE_ANCHOR) {
-        float logit[kMaxAnchor];
-#pragma unroll
-        for (int a = 0; a < kMaxAnchor; ++a) logit[a] = 0.f;
-        const float* v = sV + tid * ldv;
-        for (int e = 0; e < E; e += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(v + e);
-#pragma unroll
-          for (int a = 0; a < kMaxAnchor; ++a)
-            if (a < p.n_anchor) {
-              const float* an = sAux + a * E + e;
-              logit[a] = fmaf(x.x, an[0], logit[a]);
-              logit[a] = fmaf(x.y, an[1], logit[a]);
-              logit[a] = fmaf(x.z, an[2], logit[a]);
-              logit[a] = fmaf(x.w, an[3], logit[a]);
-            }
-        }
-        for (int s = 0; s < p.n_sub; ++s) {     // eq.6: softmax over the subset's anchors
-          float l[kAttMaxC];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < kAttMaxC; ++c)
-            if (c < C) {
-              const int a = p.subsets[s * kAttMaxC + c];
-              float lv = logit[0];
-#pragma unroll
-              for (int q = 1; q < kMaxAnchor; ++q) lv = a == q ? logit[q] : lv;
-              l[c] = lv;
-              mx = fmaxf(mx, lv);
-            }
-          float den = 0.f;
-#pragma unroll
-          for (int c = 0; c < kAttMaxC; ++c)
-            if (c < C) { l[c] = expf(l[c] - mx); den += l[c]; }
-          const float inv = 1.f / den;
-#pragma unroll
-          for (int c = 0; c < kAttMaxC; ++c)
-            if (c < C) w[s * C + c] = l[c] * inv;
-        }
-      } else {   // k-means: nearest centroid, first minimum on ties
-        const float* v = sV + tid * ldv;
-        int k = 0;
-        float best = INFINITY;
-        for (int c = 0; c < C; ++c) {
-          float d = 0.f;
-          for (int e = 0; e < E; ++e) {
-            const float t = v[e] - sAux[c * E + e];
-            d = fmaf(t, t, d);
-          }
-          if (d < best) { best = d; k = c; }
-        }
-        for (int c = 0; c < C; ++c) w[c] = c == k ? 1.f : 0.f;
-      }
-    }
+    if (tid < kTile)   // phase 1: row weights of bin tf0 + tid
+      row_weights<MODE>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * R);
     __syncthreads();
     // phase 2: acc[r][q] += Wt[tf][r] * V[tf][4q..4q+3]
 #pragma unroll
@@ -267,8 +354,30 @@ static size_t att_smem_bytes(int E, int R, int n_aux) {
   return (tile > red ? tile : red) * sizeof(float);
 }
 
+template <int MODE, int NQ>
+static int launch_partial_rt(AttParams& p, int B, int n_aux, cudaStream_t st) {
+  size_t tile = (size_t)kTileRT * p.ldv + (size_t)kTileRT * p.R + n_aux;
+  size_t red = (size_t)256 * (4 * NQ + 4);
+  const size_t smem = (tile > red ? tile : red) * sizeof(float);
+  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "attractor: %zu B of shared memory needed", smem);
+  DANET_CUDA(cudaFuncSetAttribute(attractor_partial_rt_kernel<MODE, NQ>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attractor_partial_rt_kernel<MODE, NQ><<<dim3(kParts, B), 256, smem, st>>>(p);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
 template <int MODE>
 static int launch_partial(AttParams& p, int B, int n_aux, cudaStream_t st) {
+  if (p.R <= 256) {   // register-tiled fast path for the embedding sizes in use
+    switch (p.E) {
+      case 4: return launch_partial_rt<MODE, 1>(p, B, n_aux, st);
+      case 12: return launch_partial_rt<MODE, 3>(p, B, n_aux, st);
+      case 20: return launch_partial_rt<MODE, 5>(p, B, n_aux, st);
+      case 40: return launch_partial_rt<MODE, 10>(p, B, n_aux, st);
+      default: break;
+    }
+  }
   const size_t smem = att_smem_bytes(p.E, p.R, n_aux);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "attractor: %zu B of shared memory needed", smem);
   DANET_CUDA(cudaFuncSetAttribute(attractor_partial_kernel<MODE>,

@@ -35,7 +35,7 @@ constexpr int kMaxCta = 12;           // cluster size limit (TMEM: 32 + 2*16*nct
 constexpr int kHBlock = 2048;
 constexpr int kXchLd = 17;
 constexpr int kEpiThreads = 128;
-constexpr int kThreads = 160;         // 4 epilogue warps + 1 MMA warp
+constexpr int kThreads = 160 + 32 * kMaxCta;   // 4 epilogue warps + 1 MMA warp + one sender warp per peer
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 32;          // accumulator: columns [0,16) of the first 32
 
@@ -121,7 +121,7 @@ lstm_tc_kernel(const LstmTcParams p) {
   const int unit0 = rank * kUnits;
   const int b0 = bt * NB;
   const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
-                       (tid == 0 || warp == 4);
+                       (tid == 0 || warp == 4 || warp == 5);
 
   if (tid == 0) {
     // one arrival (+ expect_tx) per source CTA and phase, posted remotely by the sender itself
@@ -200,7 +200,7 @@ lstm_tc_kernel(const LstmTcParams p) {
         DANET_PROF(2);
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ================= epilogue warps: TMEM lane m = 32*warp + lane = 4*unit + gate =================
     const int m = tid;
     // cell-update ownership: utterance bl = lane % NB, units ub..ub+UPT-1 of this warp's 8 units
@@ -235,15 +235,6 @@ lstm_tc_kernel(const LstmTcParams p) {
     const int outw = p.n_dir * H;
     float* xw = sXch + m * kXchLd;
     const uint32_t stage_off = sw64_offset(bl, ub);      // UPT contiguous bf16: units ub.. of utterance bl
-    // broadcast: warp w ships this CTA's slice to peers rank+w, rank+w+4, rank+w+8 (one elected lane each)
-    uint32_t peer_dst[3], peer_bar[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int peer = (rank + warp + 4 * i) % ncta;
-      peer_dst[i] = mapa(smem_u32(sH + (size_t)rank * kHBlock), peer);
-      peer_bar[i] = mapa(smem_u32(h_full), peer);
-    }
-
     for (int s = 0; s < T; ++s) {
       const int to = dir ? T - 1 - s : s;
       float a[UPT][4];                                   // [unit][gate]
@@ -297,20 +288,9 @@ lstm_tc_kernel(const LstmTcParams p) {
           *reinterpret_cast<uint32_t*>(st + 512 + stage_off) = pack_bf16(lo[0], lo[1]);
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        // hand the staged slice to the sender warps (producer side of named barrier 1: no wait)
+        asm volatile("bar.arrive 1, %0;" ::"r"(kEpiThreads + 32 * ncta) : "memory");
         DANET_PROF(8);
-        {
-          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kHBlock;
-          const uint32_t bar_off = (uint32_t)(s & 1) * 8;
-          const uint32_t src = smem_u32(st);
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            if (warp + 4 * i < ncta && elect_one_sync()) {
-              mbar_arrive_expect_tx_cluster(peer_bar[i] + bar_off, kSendBytes);
-              dsmem_bulk_copy(peer_dst[i] + boff, src, kSendBytes, peer_bar[i] + bar_off);
-            }
-        }
-        DANET_PROF(9);
       }
       if (valid) {
         float* o = p.out + ((size_t)b * T + to) * outw + dir * H + unit;
@@ -323,6 +303,23 @@ lstm_tc_kernel(const LstmTcParams p) {
           if (cs) *reinterpret_cast<float2*>(cs) = make_float2(c[0], c[1]);
         }
       }
+    }
+  }
+  if (warp >= 5 && warp - 5 < ncta) {
+    // ================= sender warps: warp 5+i ships this CTA's slice of h_s to peer rank+i =================
+    const int peer = (rank + (warp - 5)) % ncta;
+    const uint32_t peer_dst = mapa(smem_u32(sH + (size_t)rank * kHBlock), peer);
+    const uint32_t peer_bar = mapa(smem_u32(h_full), peer);
+    for (int s = 0; s + 1 < T; ++s) {
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads + 32 * ncta) : "memory");
+      if (elect_one_sync()) {
+        const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kHBlock;
+        const uint32_t bar = peer_bar + (uint32_t)(s & 1) * 8;
+        mbar_arrive_expect_tx_cluster(bar, kSendBytes);     // one arrival + the byte count, posted by the sender
+        dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (s & 1) * kHBlock), kSendBytes, bar);
+        DANET_PROF(9);
+      }
+      __syncwarp();
     }
   }
   // nobody leaves while a peer may still read this CTA's staging tile or signal its barriers

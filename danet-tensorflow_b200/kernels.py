@@ -73,14 +73,19 @@ def stft(wav, want_logmag=False):
     return (spec, logmag) if want_logmag else spec
 
 
-def istft(spec):
+def istft(spec, out=None):
     """spec c64 [..., T, 129] -> wav f32 [..., 64*T] with utils.istft semantics [app/utils.py:53-75]"""
     spec = _req(spec, 'spec', torch.complex64)
     if spec.dim() < 2 or spec.shape[-1] != FEATURE:
         raise ValueError('spec: expected [..., T, 129], got %s' % (tuple(spec.shape),))
     lead, T = spec.shape[:-2], spec.shape[-2]
     n_sig = int(torch.Size(lead).numel())
-    wav = torch.empty(lead + (FFT_STRIDE * T,), dtype=torch.float32, device=spec.device)
+    if out is None:
+        wav = torch.empty(lead + (FFT_STRIDE * T,), dtype=torch.float32, device=spec.device)
+    else:
+        wav = out
+        if tuple(wav.shape) != tuple(lead) + (FFT_STRIDE * T,) or wav.dtype != torch.float32 or not wav.is_contiguous():
+            raise ValueError('istft: out must be a contiguous float32 %s' % (tuple(lead) + (FFT_STRIDE * T,),))
     _lib.check(_lib.load().danet_istft_fwd(_p(spec), n_sig, T, _p(wav), _stream()), 'istft')
     _count()
     return wav

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import kernels as K
+from . import shard
 from . import modules as _modules   # noqa: F401  (registers the plugins, like app/__init__.py:1-5)
 from .hparams import hparams
 
@@ -27,6 +28,10 @@ class Model(object):
         self.infer_estimator = None
         self.separator = None
         self.s_states_di = {}             # main.py:110-121 -- zero state, never assigned
+        self._stagger_pending = False
+        self._stagger_event = None
+        self._streams = []
+        self._graphs = {}
 
     # ---------------------------------------------------------------- variables
     def get_variable(self, name, shape, init):
@@ -83,6 +88,9 @@ class Model(object):
         pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
         K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
         K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))
+        if self._stagger_pending:          # see separate(): the next stream group may start now
+            self._stagger_pending = False
+            self._stagger_event = torch.cuda.current_stream().record_event()
         return K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
 
     # ---------------------------------------------------------------- assembly
@@ -178,16 +186,81 @@ class Model(object):
         out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=('sep',))
         return out['sep']
 
-    def separate(self, wav):
-        """demo path (main.py:660-695): waveforms [B,N] f32 on the device -> [B,C,64*T] f32.
-        STFT (app/utils.py:117-122), infer graph, iSTFT per source (app/utils.py:53-75)."""
-        mix, logmag = K.stft(wav, want_logmag=True)
-        return K.istft(self.infer(mix, logmag=logmag))
+    PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
+    PIPELINE_MAX_GROUPS = 4
 
-    def separate_host(self, wav_host, out_host=None):
+    def separate(self, wav, groups=None):
+        """demo path (main.py:660-695): waveforms [B,N] f32 on the device -> [B,C,64*T] f32.
+        STFT (app/utils.py:117-122), infer graph, iSTFT per source (app/utils.py:53-75).
+
+        Utterances are independent, and the recurrence is latency-bound on a fraction of the SMs, so
+        the batch is cut into groups that run the encoder / estimator / separator on their own CUDA
+        streams: one group's dense layers fill the SMs another group's recurrence leaves idle."""
+        B = wav.shape[0]
+        if groups is None:
+            groups = max(1, min(self.PIPELINE_MAX_GROUPS, B // self.PIPELINE_GROUP))
+        mix, logmag = K.stft(wav, want_logmag=True)
+        if groups <= 1:
+            return K.istft(self.infer(mix, logmag=logmag))
+        Cn, T = hparams.MAX_N_SIGNAL, mix.shape[1]
+        out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=wav.device)
+        main = torch.cuda.current_stream()
+        fork = main.record_event()
+        streams = self._side_streams(groups)
+        prev = None
+        for g, st in enumerate(streams):
+            lo, hi = shard.shard_bounds(B, g, groups)
+            st.wait_event(fork)
+            if prev is not None:
+                # stagger: group g starts once group g-1 has queued its first dense layer, so the groups
+                # do not march in lockstep (all dense, then all recurrent) but interleave the two phases
+                st.wait_event(prev)
+            with torch.cuda.stream(st):
+                self._stagger_pending, self._stagger_event = True, None
+                K.istft(self.infer(mix[lo:hi], logmag=logmag[lo:hi]), out=out[lo:hi])
+                prev = self._stagger_event
+                self._stagger_pending = False
+        for st in streams:
+            main.wait_stream(st)
+        return out
+
+    def separate_graphed(self, wav, groups=None):
+        """`separate` replayed from a CUDA graph captured once per input shape: ~100 kernel launches
+        and their host-side argument checks collapse into one graph launch.  Returns a static output
+        buffer that the next call overwrites."""
+        key = (tuple(wav.shape), groups)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = torch.empty_like(wav)
+            static_in.copy_(wav)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                     # warm up: variables, function attributes, allocator
+                    self.separate(static_in, groups)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.separate(static_in, groups)
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        if wav.data_ptr() != static_in.data_ptr():
+            static_in.copy_(wav, non_blocking=True)
+        graph.replay()
+        return static_out
+
+    def _side_streams(self, n):
+        pool = self._streams
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=self.device))
+        return pool[:n]
+
+    def separate_host(self, wav_host, out_host=None, graphed=True):
         """The call a user makes: pinned host waveforms in, host waveforms out."""
         wav = wav_host.to(self.device, non_blocking=True)
-        y = self.separate(wav)
+        y = self.separate_graphed(wav) if graphed else self.separate(wav)
         if out_host is None:
             return y.cpu()
         out_host.copy_(y, non_blocking=True)

@@ -27,17 +27,17 @@ def wrap(name):
         events.setdefault(key, []).append((e0, e1))
         return r
     setattr(K, name, g)
-for n in ('stft', 'istft', 'center', 'linear', 'lstm_seq', 'attractor_anchor', 'mask_cmul', 'mix_features'):
+for n in ("stft", "istft", "center", "linear", "lstm_seq", "attractor_anchor", "mask_cmul", "mix_features"):
     wrap(n)
 for _ in range(3):
-    model.separate(wav)
+    model.separate(wav, groups=int(os.environ.get("GROUPS", "1")))
 torch.cuda.synchronize()
 on[0] = True
 steps = 5
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
 for _ in range(steps):
-    model.separate(wav)
+    model.separate(wav, groups=int(os.environ.get("GROUPS", "1")))
 t1.record()
 torch.cuda.synchronize()
 tot = 0.

@@ -26,6 +26,9 @@ PROTOTYPES = {
     'danet_center_fwd': (c_i, [c_f, c_i, c_ll, c_f, c_f, c_v]),
     'danet_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'danet_linear_fwd': (c_i, [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
+    'danet_gemm_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
+    'danet_gemm': (c_i, [c_f, c_ll, c_i, c_i, c_i, c_f, c_ll, c_i, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_i,
+                         c_v, c_sz, c_v]),
     'danet_lstm_seq_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
     'danet_lstm_seq_fwd': (c_i, [c_f, C.POINTER(C.c_void_p), c_ll, c_f, c_f, c_i, c_i, c_i, c_i,
                                  c_v, c_sz, c_i, c_v]),

@@ -42,16 +42,29 @@ split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int 
   }
 }
 
+// src is [K rows, R cols] row-major (reduction index k along rows) -> out[r][k] hi rows [0,R), lo rows
+// [R,2R); 32x32 tiles through smem.  perm_T > 0: reduction index k = t*nb + b (time-major) reads source row
+// b*perm_T + t + shift (batch-major source), zero when t + shift falls outside [0, perm_T): this pairs a
+// [B,T,*] tensor (optionally shifted by one step) with a [T,B,*] one.
 __global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N, int Kp,
+split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N, int Kp, int perm_T, int shift,
                        __nv_bfloat16* __restrict__ out) {
-  // W [K,N] row-major -> out[n][k] hi rows [0,N), lo rows [N,2N); 32x32 tiles through smem
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nb = perm_T > 0 ? K / perm_T : 0;
   for (int r = ty; r < 32; r += 8) {
     const int k = k0 + r, n = n0 + tx;
-    tile[r][tx] = (k < K && n < N) ? __ldg(W + (size_t)k * ldw + n) : 0.f;
+    float v = 0.f;
+    if (k < K && n < N) {
+      if (perm_T > 0) {
+        const int t = k / nb + shift, b = k % nb;
+        if (t >= 0 && t < perm_T) v = __ldg(W + ((size_t)b * perm_T + t) * ldw + n);
+      } else {
+        v = __ldg(W + (size_t)k * ldw + n);
+      }
+    }
+    tile[r][tx] = v;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
@@ -69,7 +82,9 @@ split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N,
 struct GemmParams {
   const float* bias;
   float* C;
+  long long ldc;
   int M, N, n_kblocks, T, nb;   // T > 0: logical row b*T+t is stored at row t*nb+b
+  int accumulate;               // C += instead of C =
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -148,8 +163,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int row = m0 + 32 * q + lane;
     const bool row_ok = row < p.M;
     const size_t orow = p.T > 0 ? (size_t)(row % p.T) * p.nb + row / p.T : (size_t)row;
-    float* crow = p.C + orow * p.N;
-    const bool vec = (p.N & 3) == 0;
+    float* crow = p.C + orow * p.ldc;
+    const bool vec = (p.ldc & 3) == 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < kTN; c0 += 32) {
       if (n0 + c0 >= p.N) break;                       // warp-uniform
@@ -164,13 +179,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             }
+            if (p.accumulate) {
+              const float4 cc = *reinterpret_cast<const float4*>(crow + n0 + c0 + j);
+              o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+            }
             *reinterpret_cast<float4*>(crow + n0 + c0 + j) = o;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
-            if (n < p.N) crow[n] = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+            if (n < p.N) crow[n] = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f) + (p.accumulate ? crow[n] : 0.f);
           }
         }
       }
@@ -218,42 +237,94 @@ size_t linear_tc_workspace_bytes(int M, int N, int K) {
   return ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024 + (size_t)2 * N * Kp * 2 + 1024;
 }
 
-int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, float* C,
-                  int M, int N, int K, int time_major_T, void* workspace, size_t workspace_bytes,
-                  cudaStream_t stream) {
-  DANET_REQUIRE(workspace, DANET_E_ARG, "linear: tcgen05 backend needs a workspace");
-  DANET_REQUIRE(workspace_bytes >= linear_tc_workspace_bytes(M, N, K), DANET_E_WORKSPACE,
-                "linear: workspace %zu < %zu", workspace_bytes, linear_tc_workspace_bytes(M, N, K));
-  DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "linear: C and bias must be 16-byte aligned");
-  const int Kp = pad_k(K);
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
-  __nv_bfloat16* A2 = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* W2 = reinterpret_cast<__nv_bfloat16*>(ws + ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024);
-  {
-    const long long total = (long long)M * (Kp / 2);
+struct GemmOperand {
+  const float* ptr;
+  long long ld;
+  int trans;     // 0: stored [rows = own index, cols = K]; 1: stored [rows = K, cols = own index]
+  int perm_T;    // trans == 1 only: K index is time-major over a batch-major source (see split_transpose_kernel)
+  int shift;     // with perm_T: time shift of the source row, zero filled
+};
+
+static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloat16* out, cudaStream_t stream) {
+  if (op.trans == 0) {
+    const long long total = (long long)R * (Kp / 2);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(A, lda, M, K, Kp, A2);
-    DANET_LAUNCH_CHECK();
-    dim3 g(Kp / 32, (N + 31) / 32);
-    split_transpose_kernel<<<g, 256, 0, stream>>>(W, ldw, K, N, Kp, W2);
-    DANET_LAUNCH_CHECK();
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op.ptr, op.ld, R, K, Kp, out);
+  } else {
+    dim3 g(Kp / 32, (R + 31) / 32);
+    split_transpose_kernel<<<g, 256, 0, stream>>>(op.ptr, op.ld, K, R, Kp, op.perm_T, op.shift, out);
   }
-  CUtensorMap map_a, map_b;
-  int rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+// C[M,N] (ldc) (+)= A'[M,K] * B'[K,N] (+ bias), A' / B' described by GemmOperand
+int gemm_tc(const GemmOperand& A, const GemmOperand& B, const float* bias, float* C, long long ldc, int M, int N,
+            int K, int out_perm_T, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DANET_REQUIRE(workspace, DANET_E_ARG, "gemm: the tcgen05 backend needs a workspace");
+  DANET_REQUIRE(workspace_bytes >= linear_tc_workspace_bytes(M, N, K), DANET_E_WORKSPACE,
+                "gemm: workspace %zu < %zu", workspace_bytes, linear_tc_workspace_bytes(M, N, K));
+  DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "gemm: C and bias must be 16-byte aligned");
+  const int Kp = pad_k(K);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* A2 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* B2 = reinterpret_cast<__nv_bfloat16*>(ws + ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024);
+  int rc = split_operand(A, M, K, Kp, A2, stream);
   if (rc) return rc;
-  rc = make_tensor_map_bf16(&map_b, W2, 2ll * N, Kp, kTN);
+  // B' is [K,N]: "own index" N; stored [K,N] means rows = K, i.e. the transposing split
+  GemmOperand Bt = B;
+  Bt.trans = B.trans ? 0 : 1;
+  rc = split_operand(Bt, N, K, Kp, B2, stream);
+  if (rc) return rc;
+  CUtensorMap map_a, map_b;
+  rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
+  if (rc) return rc;
+  rc = make_tensor_map_bf16(&map_b, B2, 2ll * N, Kp, kTN);
   if (rc) return rc;
   GemmParams p;
-  p.bias = bias; p.C = C; p.M = M; p.N = N; p.n_kblocks = Kp / kTK;
-  p.T = time_major_T; p.nb = time_major_T > 0 ? M / time_major_T : 0;
+  p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.n_kblocks = Kp / kTK;
+  p.T = out_perm_T; p.nb = out_perm_T > 0 ? M / out_perm_T : 0;
+  p.accumulate = accumulate;
   DANET_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
   dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
-  DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "linear: M %d too large", M);
+  DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "gemm: M %d too large", M);
   gemm_bf16x3_kernel<<<grid, 256, kGemmSmem, stream>>>(map_a, map_b, p);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
 
+int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, float* C,
+                  int M, int N, int K, int time_major_T, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+  GemmOperand a = {A, lda, 0, 0, 0}, b = {W, ldw, 0, 0, 0};
+  return gemm_tc(a, b, bias, C, N, M, N, K, time_major_T, 0, workspace, workspace_bytes, stream);
+}
+
 }  // namespace danet
+
+using namespace danet;
+
+extern "C" size_t danet_gemm_workspace_bytes(int M, int N, int K) {
+  if (M < 1 || N < 1 || K < 1) return 256;
+  return linear_tc_workspace_bytes(M, N, K);
+}
+
+extern "C" int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shiftA, const float* B,
+                          long long ldb, int transB, const float* bias, float* C, long long ldc, int M, int N,
+                          int K, int out_perm_T, int accumulate, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  DANET_REQUIRE(A && B && C, DANET_E_ARG, "gemm: null pointer");
+  DANET_REQUIRE(M >= 0 && N >= 1 && K >= 1 && ldc >= N, DANET_E_SHAPE, "gemm: M %d N %d K %d ldc %lld", M, N, K, ldc);
+  DANET_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N), DANET_E_SHAPE, "gemm: lda %lld ldb %lld", lda, ldb);
+  DANET_REQUIRE(permA_T == 0 || (transA && K % permA_T == 0 && shiftA >= -1 && shiftA <= 1), DANET_E_ARG,
+                "gemm: permA_T %d needs transA and K %% T == 0, shift in [-1,1]", permA_T);
+  DANET_REQUIRE(permA_T > 0 || shiftA == 0, DANET_E_ARG, "gemm: shiftA needs permA_T");
+  DANET_REQUIRE(out_perm_T >= 0 && (out_perm_T == 0 || M % out_perm_T == 0), DANET_E_SHAPE,
+                "gemm: M %d is not a multiple of out_perm_T %d", M, out_perm_T);
+  if (M == 0) return DANET_OK;
+  GemmOperand a = {A, lda, transA ? 1 : 0, permA_T, shiftA}, b = {B, ldb, transB ? 1 : 0, 0, 0};
+  return gemm_tc(a, b, bias, C, ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, workspace, workspace_bytes,
+                 as_stream(stream));
+}

@@ -155,6 +155,46 @@ def linear(a, w, bias=None, time_major_T=0, backend=None, k_rows=None, row_offse
     return out
 
 
+def gemm(a, b, trans_a=False, trans_b=False, bias=None, out=None, ldc=None, perm_a_T=0, shift_a=0, out_perm_T=0,
+         accumulate=False, m=None, n=None, k=None, lda=None, ldb=None):
+    """
+    General tensor-core product of the training step: C[M,N] (+)= A'[M,K] @ B'[K,N] (+ bias).
+    `a` / `b` are 2-D float32 tensors (or views with a row stride); sizes default to their shapes.
+    See include/danet.h (danet_gemm) for perm / shift / out_perm.
+    """
+    a = _req_strided(a, 'a')
+    b = _req_strided(b, 'b')
+    lda = a.stride(0) if lda is None else lda
+    ldb = b.stride(0) if ldb is None else ldb
+    M = (a.shape[1] if trans_a else a.shape[0]) if m is None else m
+    Kd = (a.shape[0] if trans_a else a.shape[1]) if k is None else k
+    N = (b.shape[0] if trans_b else b.shape[1]) if n is None else n
+    kb = b.shape[1] if trans_b else b.shape[0]
+    if k is None and kb != Kd:
+        raise ValueError('gemm: reduction sizes differ (%d vs %d)' % (Kd, kb))
+    if out is None:
+        if accumulate:
+            raise ValueError('gemm: accumulate needs out')
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ldc = out.stride(0) if ldc is None else ldc
+    lib = _lib.load()
+    ws = _ws(lib.danet_gemm_workspace_bytes(M, N, Kd), a.device)
+    _lib.check(lib.danet_gemm(_p(a), lda, int(trans_a), int(perm_a_T), int(shift_a), _p(b), ldb, int(trans_b),
+                              _p(bias), _p(out), ldc, M, N, Kd, int(out_perm_T), int(accumulate), _p(ws),
+                              ws.numel(), _stream()), 'gemm')
+    _count(3)
+    return out
+
+
+def _req_strided(t, name):
+    """2-D float32 CUDA tensor whose rows are contiguous (row stride >= width): views are fine"""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+        raise ValueError('%s: expected a 2-D float32 CUDA tensor' % name)
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
 def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False):
     """
     pre [n_dir,T,B,4H]; w_list = the reference's stacked [I+H,4H] matrices, one per direction

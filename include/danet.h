@@ -82,6 +82,22 @@ int danet_linear_fwd(const float* A, long long lda, const float* W, long long ld
                      int time_major_T, void* workspace, size_t workspace_bytes,
                      int backend, void* stream);
 
+/* general tensor-core product used by the training step (dX = dY*W^T, dW = X^T*dY; TF autodiff of
+ * tf.matmul at app/ops.py:77):  C[M,N] (row stride ldc) (+)= A'[M,K] * B'[K,N] (+ bias[N]).
+ *   transA = 0: A stored [M,K] (lda);  1: A stored [K,M] (lda)
+ *   transB = 0: B stored [K,N] (ldb);  1: B stored [N,K] (ldb)
+ *   permA_T > 0 (needs transA): the reduction index k = t*(K/T) + b (time-major) reads A row
+ *     b*T + t + shiftA of a batch-major [B,T,*] tensor, zero when t + shiftA leaves [0,T) --
+ *     pairs the layer input X[b,t] (shift 0) or the previous hidden state h[b,t-1] / h[b,t+1]
+ *     (shift -1 / +1) with the time-major gate gradients;
+ *   out_perm_T: row permutation of C as in danet_linear_fwd;  accumulate != 0: C += .
+ * Always tcgen05 bf16x3 (see danet_linear_fwd). */
+size_t danet_gemm_workspace_bytes(int M, int N, int K);
+int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shiftA,
+               const float* B, long long ldb, int transB, const float* bias,
+               float* C, long long ldc, int M, int N, int K, int out_perm_T, int accumulate,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------
  * replaces Model.lyr_lstm (main.py:76-132: tf.scan from zero state) over
  * ops.lyr_lstm_flat (app/ops.py:139-147: gates [cand|i|f|o], candidate WITHOUT tanh,

@@ -358,3 +358,45 @@ def test_separate_waveforms(D, backend):
     model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
     out = model.separate(cuda(wav))
     assert rel(out, ref_wav) < TOL
+
+
+# ---------------------------------------------------------------- training-side products
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_transposes(K, ta, tb):
+    rs = np.random.RandomState(7)
+    M, N, Kd = 200, 136, 333
+    a = rs.standard_normal((Kd, M) if ta else (M, Kd)).astype(np.float32)
+    b = rs.standard_normal((N, Kd) if tb else (Kd, N)).astype(np.float32)
+    ref = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    out = K.gemm(cuda(a), cuda(b), trans_a=ta, trans_b=tb)
+    assert rel(out, ref) < 3e-5
+    c0 = rs.standard_normal((M, N + 8)).astype(np.float32)       # accumulate into a strided view
+    cg = cuda(c0)
+    K.gemm(cuda(a), cuda(b), trans_a=ta, trans_b=tb, out=cg[:, :N], accumulate=True)
+    exp = c0.astype(np.float64)
+    exp[:, :N] += ref
+    assert rel(cg, exp) < 3e-5
+
+
+@pytest.mark.parametrize('shift', [0, -1, 1])
+def test_gemm_time_major_pairing(K, shift):
+    """dW = sum_{b,t} X[b,t+shift]^T dA[t,b]  (X batch-major, dA time-major, zero outside [0,T))"""
+    rs = np.random.RandomState(3)
+    B, T, I, N = 3, 11, 70, 96
+    x = rs.standard_normal((B, T, I)).astype(np.float32)
+    da = rs.standard_normal((T, B, N)).astype(np.float32)
+    xs = np.zeros_like(x)
+    if shift == 0:
+        xs = x
+    elif shift == -1:
+        xs[:, 1:] = x[:, :-1]
+    else:
+        xs[:, :-1] = x[:, 1:]
+    ref = np.einsum('bti,tbn->in', xs.astype(np.float64), da.astype(np.float64))
+    out = K.gemm(cuda(x).view(B * T, I), cuda(da).view(T * B, N), trans_a=True, perm_a_T=T, shift_a=shift)
+    assert rel(out, ref) < 3e-5
+    # dX = dA * W^T with time-major rows written back batch-major
+    w = rs.standard_normal((I, N)).astype(np.float32)
+    ref_dx = np.einsum('tbn,in->bti', da.astype(np.float64), w.astype(np.float64))
+    dx = K.gemm(cuda(da).view(T * B, N), cuda(w), trans_b=True, out_perm_T=B)
+    assert rel(dx.view(B, T, I), ref_dx) < 3e-5

@@ -33,10 +33,14 @@ PROTOTYPES = {
     'danet_lstm_seq_fwd': (c_i, [c_f, C.POINTER(C.c_void_p), c_ll, c_f, c_f, c_i, c_i, c_i, c_i,
                                  c_v, c_sz, c_i, c_v]),
     'danet_attractor_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
-    'danet_attractor_truth_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
+    'danet_attractor_truth_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
     'danet_anchor_num_subsets': (c_i, [c_i, c_i]),
-    'danet_attractor_anchor_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_v, c_i, c_i, c_i, c_i, c_i,
+    'danet_attractor_anchor_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_v, c_f, c_i, c_i, c_i, c_i, c_i,
                                          c_v, c_sz, c_v]),
+    'danet_head_bwd_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
+    'danet_head_bwd_attractors': (c_i, [c_f, c_f, c_f, c_f, c_v, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
+    'danet_head_bwd_embed': (c_i, [c_f, c_f, c_f, c_f, c_v, c_f, c_i, c_f, c_f, c_f, c_v, c_f, c_f, c_f,
+                                   c_i, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
     'danet_attractor_kmeans_fwd': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
     'danet_mask_cmul_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_istft_fwd': (c_i, [c_f, c_i, c_i, c_f, c_v]),

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256)
 attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, int nQ, int n_sub,
                           float denom_add, float* __restrict__ attractors,
                           float* __restrict__ attractor_sets, float* __restrict__ sims,
-                          int* __restrict__ choice) {
+                          int* __restrict__ choice, float* __restrict__ den_out) {
   __shared__ float s_sum[kAttMaxRows * (kAttMaxE + 4)];
   __shared__ float s_sim[32];
   __shared__ int s_choice;
@@ -292,6 +292,8 @@ attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, i
     s_sum[i] = s;
   }
   __syncthreads();
+  if (den_out)   // raw weight sums per row, kept for the backward pass
+    for (int r = tid; r < R; r += 256) den_out[(size_t)b * R + r] = s_sum[r * ld + E];
   if (MODE == MODE_TRUTH) {
     for (int i = tid; i < C * E; i += 256) {
       const int c = i / E, e = i % E;
@@ -415,7 +417,7 @@ extern "C" size_t danet_attractor_workspace_bytes(int B, int n_acc_rows, int E) 
 extern "C" int danet_anchor_num_subsets(int n_anchor, int C) { return n_choose_k(n_anchor, C); }
 
 extern "C" int danet_attractor_truth_fwd(const float* embed, const float* src_pwr, const float* mix_pwr,
-                                         float* attractors, int B, int C, int TF, int E, int mode,
+                                         float* attractors, float* den, int B, int C, int TF, int E, int mode,
                                          void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common("attractor_truth", embed, B, C, TF, E, C, workspace, workspace_bytes);
   if (rc) return rc;
@@ -430,14 +432,14 @@ extern "C" int danet_attractor_truth_fwd(const float* embed, const float* src_pw
   rc = launch_partial<MODE_TRUTH>(p, B, 0, as_stream(stream));
   if (rc) return rc;
   attractor_finalize_kernel<MODE_TRUTH><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr);
+      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr, den);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
 
 extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* anchors, float* attractors,
                                           float* attractor_sets, float* similarities, int* choice,
-                                          int B, int C, int TF, int E, int n_anchor, void* workspace,
+                                          float* den, int B, int C, int TF, int E, int n_anchor, void* workspace,
                                           size_t workspace_bytes, void* stream) {
   DANET_REQUIRE(n_anchor >= C && n_anchor <= kMaxAnchor, DANET_E_SHAPE,
                 "attractor_anchor: n_anchor %d (C %d .. %d)", n_anchor, C, kMaxAnchor);
@@ -466,7 +468,7 @@ extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* ancho
   rc = launch_partial<MODE_ANCHOR>(p, B, n_anchor * E, as_stream(stream));
   if (rc) return rc;
   attractor_finalize_kernel<MODE_ANCHOR><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice);
+      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice, den);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
@@ -486,7 +488,7 @@ extern "C" int danet_attractor_kmeans_fwd(const float* embed, float* centroids, 
     rc = launch_partial<MODE_KMEANS>(p, B, C * E, as_stream(stream));
     if (rc) return rc;
     attractor_finalize_kernel<MODE_KMEANS><<<B, 256, 0, as_stream(stream)>>>(
-        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr);
+        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr, nullptr);
     DANET_LAUNCH_CHECK();
   }
   return DANET_OK;

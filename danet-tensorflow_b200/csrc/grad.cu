@@ -125,7 +125,7 @@ head_bwd_kernel(const GradParams p) {
   float* sBasis = sCoef + kGTile * J;                // [J][E]        pass 2: d_embed basis vectors
   float* sA = sBasis + J * E;                        // [C][E] attractors
   float* sAn = sA + kGMaxC * E;                      // [C][E] chosen anchors (anchor mode)
-  float* sK = sAn + kGMaxC * E;                      // [2*C] dden_c, 1/(den_c [+eps])
+  float* sK = sAn + kGMaxC * E;                      // [C] d_den_c = -(d_attr_c . A_c) / den_c
   const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x;
   const long long TF = p.TF;
   const float* Vb = p.embed + (size_t)b * TF * E;
@@ -212,7 +212,7 @@ head_bwd_kernel(const GradParams p) {
               d = fmaf(v[e], sBasis[(C + c) * E + e], d);
             }
             l[c] = a;
-            dS[c] = d + sK[c] / p.den[((size_t)b * p.n_sub + p.choice[b]) * C + c];
+            dS[c] = d + sK[c];
             mx = fmaxf(mx, a);
           }
           float den = 0.f;

@@ -1,0 +1,194 @@
+// K6 (part): backward-through-time of the (Bi)LSTM layer -- what TF derives for the tf.scan of
+// main.py:125-131 over ops.lyr_lstm_flat (app/ops.py:139-147):
+//   forward   a = pre + h_{t-1} Wh ; g = a_g (no tanh) ; i,f,o = sigmoid ; c = i g + f c_{t-1} ; h = o tanh(c)
+//   backward  dh = d_out_t + da_{t+1} Wh^T
+//             dc = dh o (1 - tanh(c)^2) + dc_{t+1} f_{t+1}
+//             da_g = dc i ; da_i = dc g i(1-i) ; da_f = dc c_{t-1} f(1-f) ; da_o = dh tanh(c) o(1-o)
+// The forward kernel leaves the post-activation gates [g|i|f|o] in the pre-activation buffer and the cell
+// states in cell_seq; this kernel walks the sequence in reverse and overwrites the gates with da in place
+// (the dW = X^T da / dX = da W^T products are danet_gemm calls on that buffer).
+// Exact fp32, persistent cooperative kernel: a CTA owns 16 hidden units x 16 utterances of one direction,
+// keeps its 16 rows of Wh (16 x 4H) in shared memory, and per step pulls the group's da_{t+1} [16 x 4H]
+// through L2 (release/acquire counter, as lstm.cu).  A tcgen05 cluster version is the next step.
+#include "common.cuh"
+
+namespace danet {
+
+constexpr int kBU = 16;     // hidden units per CTA
+constexpr int kBB = 16;     // utterances per CTA
+constexpr int kKS = 4;      // split of the 4H reduction across lanes
+
+__device__ __forceinline__ int ld_acquire_i(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct LstmBwdParams {
+  const float* d_out;      // [B][T][n_dir*H]
+  float* gates;            // [n_dir][T][B][4H]: in gates [g|i|f|o], out da
+  const float* cell_seq;   // [n_dir][T][B][H]
+  const float* Wh[2];      // recurrent rows [H][4H] (row stride ldw)
+  long long ldw;
+  int* counters;           // [n_dir][n_bt]
+  int n_dir, T, B, H, bt0, n_bt_total;
+};
+
+__global__ void __launch_bounds__(256)
+lstm_bwd_kernel(LstmBwdParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, T = p.T, B = p.B, G4 = 4 * H;
+  float* sW = smem;                        // [kBU][4H]
+  float* sD = sW + (size_t)kBU * G4;       // [kBB][4H]  da_{t+1} of this batch tile
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int n_chunks = gridDim.x;
+  const int u0 = chunk * kBU, b0 = bt * kBB;
+
+  const float* Wg = p.Wh[dir];
+  for (int i = tid; i < kBU * (G4 / 4); i += 256) {
+    const int u = i / (G4 / 4), q = i % (G4 / 4);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u0 + u < H) w = __ldg(reinterpret_cast<const float4*>(Wg + (size_t)(u0 + u) * p.ldw) + q);
+    reinterpret_cast<float4*>(sW)[i] = w;
+  }
+  // thread -> 2 utterances x 2 units, one quarter of the 4H reduction; 64 tiles x 4 quarters
+  const int ks = tid & (kKS - 1), tile = tid >> 2;
+  const int tb = (tile & 7) * 2, tu = (tile >> 3) * 2;          // local utterance / unit of the 2x2 tile
+  const int kq = (G4 / 4 + kKS - 1) / kKS;                      // float4 per quarter (ceil)
+  const int q_lo = ks * kq, q_hi = min(G4 / 4, q_lo + kq);
+  int* counter = p.counters + dir * p.n_bt_total + bt;
+  const int outw = p.n_dir * H;
+
+  // each (utterance, unit) pair is finalised by the ks == 0 lane of its tile: it carries dc
+  float dc_next[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  __syncthreads();
+
+  for (int s = T - 1; s >= 0; --s) {       // processing index; original time of this step:
+    const int to = dir ? T - 1 - s : s;
+    float dh[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (s < T - 1) {
+      // da of processing step s+1 (original time tn) from every CTA of the group
+      const int tn = dir ? to - 1 : to + 1;
+      if (tid == 0) {
+        const int want = n_chunks * (T - 1 - s);
+        while (ld_acquire_i(counter) < want) {}
+      }
+      __syncthreads();
+      for (int i = tid; i < kBB * (G4 / 4); i += 256) {
+        const int r = i / (G4 / 4), q = i % (G4 / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + r < B)
+          v = __ldcg(reinterpret_cast<const float4*>(p.gates + (((size_t)dir * T + tn) * B + b0 + r) * G4) + q);
+        reinterpret_cast<float4*>(sD)[i] = v;
+      }
+      __syncthreads();
+      const float4* d0 = reinterpret_cast<const float4*>(sD + (size_t)tb * G4);
+      const float4* d1 = reinterpret_cast<const float4*>(sD + (size_t)(tb + 1) * G4);
+      const float4* w0 = reinterpret_cast<const float4*>(sW + (size_t)tu * G4);
+      const float4* w1 = reinterpret_cast<const float4*>(sW + (size_t)(tu + 1) * G4);
+#pragma unroll 2
+      for (int q = q_lo; q < q_hi; ++q) {
+        const float4 a0 = d0[q], a1 = d1[q], x0 = w0[q], x1 = w1[q];
+        dh[0][0] = fmaf(a0.x, x0.x, dh[0][0]); dh[0][0] = fmaf(a0.y, x0.y, dh[0][0]);
+        dh[0][0] = fmaf(a0.z, x0.z, dh[0][0]); dh[0][0] = fmaf(a0.w, x0.w, dh[0][0]);
+        dh[0][1] = fmaf(a0.x, x1.x, dh[0][1]); dh[0][1] = fmaf(a0.y, x1.y, dh[0][1]);
+        dh[0][1] = fmaf(a0.z, x1.z, dh[0][1]); dh[0][1] = fmaf(a0.w, x1.w, dh[0][1]);
+        dh[1][0] = fmaf(a1.x, x0.x, dh[1][0]); dh[1][0] = fmaf(a1.y, x0.y, dh[1][0]);
+        dh[1][0] = fmaf(a1.z, x0.z, dh[1][0]); dh[1][0] = fmaf(a1.w, x0.w, dh[1][0]);
+        dh[1][1] = fmaf(a1.x, x1.x, dh[1][1]); dh[1][1] = fmaf(a1.y, x1.y, dh[1][1]);
+        dh[1][1] = fmaf(a1.z, x1.z, dh[1][1]); dh[1][1] = fmaf(a1.w, x1.w, dh[1][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dh[i][j] += __shfl_xor_sync(0xffffffffu, dh[i][j], 1);
+          dh[i][j] += __shfl_xor_sync(0xffffffffu, dh[i][j], 2);
+        }
+    }
+    if (ks == 0) {
+      const int tp = dir ? to + 1 : to - 1;          // original time of the PREVIOUS processed state c_{t-1}
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int b = b0 + tb + i, unit = u0 + tu + j;
+          if (b < B && unit < H) {
+            float* gt = p.gates + (((size_t)dir * T + to) * B + b) * G4 + unit;
+            const float gg = gt[0], ig = gt[H], fg = gt[2 * H], og = gt[3 * H];
+            const float c = p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit];
+            const float cp = s > 0 ? p.cell_seq[(((size_t)dir * T + tp) * B + b) * H + unit] : 0.f;
+            const float dht = dh[i][j] + p.d_out[((size_t)b * T + to) * outw + dir * H + unit];
+            const float th = tanhf(c);
+            const float dc = dht * og * (1.f - th * th) + dc_next[i][j];
+            dc_next[i][j] = dc * fg;
+            __stcg(gt, dc * ig);                                  // da_g (candidate has no tanh)
+            __stcg(gt + H, dc * gg * ig * (1.f - ig));            // da_i
+            __stcg(gt + 2 * H, dc * cp * fg * (1.f - fg));        // da_f
+            __stcg(gt + 3 * H, dht * th * og * (1.f - og));       // da_o
+          }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(counter, 1);
+    }
+  }
+}
+
+static size_t lstm_bwd_smem_bytes(int H) { return (size_t)(kBU + kBB) * 4 * H * sizeof(float); }
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H) {
+  (void)H;
+  if (n_dir < 1 || B < 1) return 256;
+  return (((size_t)n_dir * ((B + kBB - 1) / kBB) * sizeof(int)) + 255) / 256 * 256;
+}
+
+extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
+                                  const float* const* host_Wh, long long ldw, int n_dir, int T, int B, int H,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  DANET_REQUIRE(d_out && gates && cell_seq && host_Wh && workspace, DANET_E_ARG, "lstm_seq_bwd: null pointer");
+  DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_seq_bwd: n_dir %d", n_dir);
+  for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_seq_bwd: null Wh[%d]", d);
+  DANET_REQUIRE(T >= 0 && B >= 0 && H >= 4 && H % 4 == 0 && ldw >= 4ll * H && ldw % 4 == 0, DANET_E_SHAPE,
+                "lstm_seq_bwd: T %d B %d H %d ldw %lld", T, B, H, ldw);
+  DANET_REQUIRE(aligned16(gates) && aligned16(host_Wh[0]), DANET_E_ALIGN, "lstm_seq_bwd: gates / Wh must be 16-byte aligned");
+  DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_bwd_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
+                "lstm_seq_bwd: workspace too small");
+  if (T == 0 || B == 0) return DANET_OK;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = lstm_bwd_smem_bytes(H);
+  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq_bwd: H %d needs %zu B of shared memory", H, smem);
+  DANET_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel, 256, smem));
+  const int n_chunks = (H + kBU - 1) / kBU;
+  const int n_bt = (B + kBB - 1) / kBB;
+  const int resident = per_sm * num_sms();
+  int bt_per_launch = resident / (n_dir * n_chunks);
+  DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE, "lstm_seq_bwd: one batch tile needs %d resident CTAs, device holds %d",
+                n_dir * n_chunks, resident);
+  if (bt_per_launch > n_bt) bt_per_launch = n_bt;
+  DANET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_dir * n_bt * sizeof(int), st));
+  LstmBwdParams p;
+  p.d_out = d_out; p.gates = gates; p.cell_seq = cell_seq;
+  p.Wh[0] = host_Wh[0];
+  p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
+  p.ldw = ldw;
+  p.counters = reinterpret_cast<int*>(workspace);
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.n_bt_total = n_bt;
+  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
+    p.bt0 = bt0;
+    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
+    void* args[] = {&p};
+    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel, dim3(n_chunks, nb, n_dir), dim3(256), args,
+                                           smem, st));
+  }
+  return DANET_OK;
+}

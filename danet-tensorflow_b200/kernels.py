@@ -243,8 +243,8 @@ def _embed_flat(embed):
 TRUTH_MODES = {'truth': 0, 'truth-threshold': 1, 'truth-weighted': 2}
 
 
-def attractor_truth(embed, src_pwr, mix_pwr, mode):
-    """[app/modules.py:390-412 / 425-450 / 462-487] -> [B,C,E]"""
+def attractor_truth(embed, src_pwr, mix_pwr, mode, return_den=False):
+    """[app/modules.py:390-412 / 425-450 / 462-487] -> [B,C,E] (+ den [B,C], the per-class weight sums)"""
     embed, B, TF, E = _embed_flat(embed)
     src_pwr = _req(src_pwr, 'src_pwr', dim=4)
     Cn = src_pwr.shape[1]
@@ -258,16 +258,17 @@ def attractor_truth(embed, src_pwr, mix_pwr, mode):
     else:
         mix_pwr = None
     out = torch.empty((B, Cn, E), dtype=torch.float32, device=embed.device)
+    den = torch.empty((B, Cn), dtype=torch.float32, device=embed.device) if return_den else None
     lib = _lib.load()
     ws = _ws(lib.danet_attractor_workspace_bytes(B, Cn, E), embed.device)
-    _lib.check(lib.danet_attractor_truth_fwd(_p(embed), _p(src_pwr), _p(mix_pwr), _p(out), B, Cn, TF, E, m,
+    _lib.check(lib.danet_attractor_truth_fwd(_p(embed), _p(src_pwr), _p(mix_pwr), _p(out), _p(den), B, Cn, TF, E, m,
                                              _p(ws), ws.numel(), _stream()), 'attractor_truth')
     _count(2)
-    return out
+    return (out, den) if return_den else out
 
 
-def attractor_anchor(embed, anchors, n_signal, return_all=False):
-    """[app/modules.py:501-545] -> [B,C,E] (+ sets [B,P,C,E], sims [B,P], choice [B] int32)"""
+def attractor_anchor(embed, anchors, n_signal, return_all=False, return_den=False):
+    """[app/modules.py:501-545] -> [B,C,E] (+ sets [B,P,C,E], sims [B,P], choice [B] int32 (+ den [B,P,C]))"""
     embed, B, TF, E = _embed_flat(embed)
     anchors = _req(anchors, 'anchors', dim=2)
     A = anchors.shape[0]
@@ -277,14 +278,18 @@ def attractor_anchor(embed, anchors, n_signal, return_all=False):
     P = lib.danet_anchor_num_subsets(A, n_signal)
     dev = embed.device
     out = torch.empty((B, n_signal, E), dtype=torch.float32, device=dev)
+    return_all = return_all or return_den
     sets = torch.empty((B, P, n_signal, E), dtype=torch.float32, device=dev) if return_all else None
     sims = torch.empty((B, P), dtype=torch.float32, device=dev) if return_all else None
     choice = torch.empty((B,), dtype=torch.int32, device=dev) if return_all else None
+    den = torch.empty((B, P, n_signal), dtype=torch.float32, device=dev) if return_den else None
     ws = _ws(lib.danet_attractor_workspace_bytes(B, max(P, 1) * n_signal, E), dev)
     _lib.check(lib.danet_attractor_anchor_fwd(_p(embed), _p(anchors), _p(out), _p(sets), _p(sims), _p(choice),
-                                              B, n_signal, TF, E, A, _p(ws), ws.numel(), _stream()),
+                                              _p(den), B, n_signal, TF, E, A, _p(ws), ws.numel(), _stream()),
                'attractor_anchor')
     _count(2)
+    if return_den:
+        return out, sets, sims, choice, den
     return (out, sets, sims, choice) if return_all else out
 
 
@@ -371,3 +376,44 @@ def pit_mse(x, y):
                                      _p(out['snr']), _p(ws), ws.numel(), _stream()), 'pit_mse')
     _count(2)
     return out
+
+
+def head_bwd(embed, attractors, mix, src, perm_idx, kind, est_mode, src_pwr=None, mix_pwr=None, anchors=None,
+             choice=None, den=None):
+    """
+    Backward of loss = pit_mse(src, mask*mix) through the separator and the estimator
+    (TF autodiff at main.py:357-358) -> dict(d_embed [B,TF,E], d_attractors [B,C,E], d_anchors [A,E] | None).
+    est_mode: 'truth' | 'truth-threshold' | 'truth-weighted' | 'anchor'.
+    """
+    embed, B, TF, E = _embed_flat(embed)
+    attractors = _req(attractors, 'attractors', dim=3)
+    mix = _req(mix, 'mix', torch.complex64, 3)
+    src = _req(src, 'src', torch.complex64, 4)
+    perm_idx = _req(perm_idx, 'perm_idx', torch.int32, 1)
+    den = _req(den, 'den')
+    Cn = attractors.shape[1]
+    k = SEPARATOR_KINDS[kind] if isinstance(kind, str) else int(kind)
+    mode = 3 if est_mode == 'anchor' else TRUTH_MODES[est_mode]
+    dev = embed.device
+    lib = _lib.load()
+    ws = _ws(lib.danet_head_bwd_workspace_bytes(B, Cn, E), dev)
+    d_attr = torch.empty((B, Cn, E), dtype=torch.float32, device=dev)
+    _lib.check(lib.danet_head_bwd_attractors(_p(embed), _p(attractors), _p(mix), _p(src), _p(perm_idx), _p(d_attr),
+                                             B, Cn, TF, E, k, _p(ws), ws.numel(), _stream()), 'head_bwd_attractors')
+    d_embed = torch.empty((B, TF, E), dtype=torch.float32, device=dev)
+    d_anchors, n_anchor = None, 0
+    if mode == 3:
+        anchors = _req(anchors, 'anchors', dim=2)
+        choice = _req(choice, 'choice', torch.int32, 1)
+        n_anchor = anchors.shape[0]
+        d_anchors = torch.empty_like(anchors)
+    else:
+        src_pwr = _req(src_pwr, 'src_pwr', dim=4)
+        if mode != 0:
+            mix_pwr = _req(mix_pwr, 'mix_pwr', dim=3)
+    _lib.check(lib.danet_head_bwd_embed(_p(embed), _p(attractors), _p(mix), _p(src), _p(perm_idx), _p(d_attr), mode,
+                                        _p(src_pwr), _p(mix_pwr), _p(anchors), _p(choice), _p(den), _p(d_embed),
+                                        _p(d_anchors), B, Cn, TF, E, k, n_anchor, _p(ws), ws.numel(), _stream()),
+               'head_bwd_embed')
+    _count(4)
+    return {'d_embed': d_embed, 'd_attractors': d_attr, 'd_anchors': d_anchors}

@@ -120,18 +120,19 @@ int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long 
  *   embed [B,TF,E], src_pwr [B,C,TF], mix_pwr [B,TF] -> attractors [B,C,E] */
 size_t danet_attractor_workspace_bytes(int B, int n_acc_rows, int E);
 int danet_attractor_truth_fwd(const float* embed, const float* src_pwr,
-                              const float* mix_pwr, float* attractors,
+                              const float* mix_pwr, float* attractors, float* den /* nullable [B,C] */,
                               int B, int C, int TF, int E, int mode,
                               void* workspace, size_t workspace_bytes, void* stream);
 /* anchor estimator replaces app/modules.py:501-545 + app/ops.py:273-292:
  * P = C(n_anchor, C) subsets in itertools.combinations order; eq.6 softmax over the
  * subset's anchors, eq.7 weighted means, eq.8 max over the full CxC Gram (diagonal
  * included), eq.9 argmin.  Outputs: attractors [B,C,E]; optional attractor_sets
- * [B,P,C,E], similarities [B,P], choice [B] int32. */
+ * [B,P,C,E], similarities [B,P], choice [B] int32, den [B,P,C] (the eq.7 denominators,
+ * kept for the backward pass; likewise den [B,C] = sum of weights in the truth family). */
 int danet_anchor_num_subsets(int n_anchor, int C);
 int danet_attractor_anchor_fwd(const float* embed, const float* anchors,
                                float* attractors, float* attractor_sets,
-                               float* similarities, int* choice,
+                               float* similarities, int* choice, float* den,
                                int B, int C, int TF, int E, int n_anchor,
                                void* workspace, size_t workspace_bytes, void* stream);
 /* k-means estimator: NEW plugin without a reference twin (README.md:216-217 lists it
@@ -157,6 +158,26 @@ int danet_mask_cmul_fwd(const float* embed, const float* attractors,
  * overlap-add of irfft(X[n])*w, division by sum(w^2) where non-zero, length 64*T.
  * spec [n_sig,T,129] complex -> wav [n_sig, 64*T] fp32. */
 int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* stream);
+/* ---- K6  backward of the separation head ---------------------------------------------
+ * What TF autodiff derives (main.py:357-358) for loss = pit_mse(src, mask*mix) with
+ * mask = softmax/sigmoid(V.A) and A = estimator(V).  perm_idx comes from danet_pit_mse_fwd;
+ * no gradient flows through argmax / argmin / the permutation choice.
+ *   pass 1: d_attractors [B,C,E] (through the mask);
+ *   pass 2: d_embed [B,TF,E] = mask path + estimator path, d_anchors [n_anchor,E].
+ * est_mode 0..2 = truth / truth-threshold / truth-weighted (needs src_pwr, mix_pwr, den [B,C]),
+ * 3 = anchor (needs anchors, choice [B], den [B,P,C], d_anchors). */
+size_t danet_head_bwd_workspace_bytes(int B, int C, int E);
+int danet_head_bwd_attractors(const float* embed, const float* attractors, const float* mix_c64,
+                              const float* src_c64, const int* perm_idx, float* d_attractors,
+                              int B, int C, int TF, int E, int kind,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int danet_head_bwd_embed(const float* embed, const float* attractors, const float* mix_c64,
+                         const float* src_c64, const int* perm_idx, const float* d_attractors,
+                         int est_mode, const float* src_pwr, const float* mix_pwr,
+                         const float* anchors, const int* choice, const float* den,
+                         float* d_embed, float* d_anchors, int B, int C, int TF, int E, int kind,
+                         int n_anchor, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K5  PIT-MSE + SNR ---------------------------------------------------------
  * replaces ops.pit_mse_loss (app/ops.py:374-431), the permutation gather at
  * main.py:293-306 and ops.batch_snr (app/ops.py:191-222).

@@ -400,3 +400,53 @@ def test_gemm_time_major_pairing(K, shift):
     ref_dx = np.einsum('tbn,in->bti', da.astype(np.float64), w.astype(np.float64))
     dx = K.gemm(cuda(da).view(T * B, N), cuda(w), trans_b=True, out_perm_T=B)
     assert rel(dx.view(B, T, I), ref_dx) < 3e-5
+
+
+def _head_case(rs, B, C, T, E):
+    V = (rs.standard_normal((B, T, 129, E)) * 0.7).astype(np.float32)
+    src = ((rs.standard_normal((B, C, T, 129)) + 1j * rs.standard_normal((B, C, T, 129))) * 20).astype(np.complex64)
+    return V, src
+
+
+@pytest.mark.parametrize('kind', ['dot-softmax-orig', 'dot-sigmoid-orig'])
+@pytest.mark.parametrize('est', ['anchor', 'truth', 'truth-threshold', 'truth-weighted'])
+@pytest.mark.parametrize('B,C,T,E', [(3, 2, 9, 20), (2, 3, 7, 12)])
+def test_head_backward(K, kind, est, B, C, T, E):
+    """d loss / d embedding, d attractors, d anchors against torch autograd on the oracle"""
+    rs = np.random.RandomState(B * 100 + C)
+    V, src = _head_case(rs, B, C, T, E)
+    anchors = rs.standard_normal((6, E)).astype(np.float32)
+    # --- oracle (float64 autograd)
+    Vt = torch.from_numpy(V).double().requires_grad_(True)
+    an = torch.from_numpy(anchors).double().requires_grad_(True)
+    srct = torch.from_numpy(src).to(torch.complex128)
+    mixt = srct.sum(1)
+    mix_pwr, src_pwr = mixt.abs(), srct.abs()
+    if est == 'anchor':
+        A = O.estimator_anchor(Vt, an, C)
+    else:
+        A = {'truth': O.estimator_truth, 'truth-threshold': O.estimator_truth_threshold,
+             'truth-weighted': O.estimator_truth_weighted}[est](Vt, src_pwr, mix_pwr)
+    A.retain_grad()
+    sep_pwr = O.separator(mix_pwr, A, Vt.reshape(B, -1, E), kind)
+    ph = torch.atan2(mixt.imag, mixt.real).unsqueeze(1)
+    sep = torch.complex(torch.cos(ph) * sep_pwr, torch.sin(ph) * sep_pwr)
+    loss, perms, idx, _ = O.pit_mse_loss(srct, sep)
+    loss.backward()
+    # --- device
+    Vg, srcg = cuda(V), cuda(src)
+    feats = K.mix_features(srcg)
+    if est == 'anchor':
+        Ag, _, _, choice, den = K.attractor_anchor(Vg, cuda(anchors), C, return_den=True)
+    else:
+        Ag, den = K.attractor_truth(Vg, feats['src_pwr'], feats['mix_pwr'], est, return_den=True)
+        choice = None
+    out = K.mask_cmul(Vg.view(B, -1, E), Ag, feats['mix'], kind, want=('sep',))
+    pit = K.pit_mse(srcg, out['sep'])
+    assert np.array_equal(pit['perm_idx'].cpu().numpy(), idx.numpy())
+    g = K.head_bwd(Vg, Ag, feats['mix'], srcg, pit['perm_idx'], kind, est, src_pwr=feats['src_pwr'],
+                   mix_pwr=feats['mix_pwr'], anchors=cuda(anchors), choice=choice, den=den)
+    assert rel(g['d_attractors'], A.grad) < 2e-4
+    assert rel(g['d_embed'].view(B, T, 129, E), Vt.grad) < 2e-4
+    if est == 'anchor':
+        assert rel(g['d_anchors'], an.grad) < 2e-4

@@ -12,7 +12,7 @@
 namespace danet {
 
 int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out,
-                float* cell_seq, int n_dir, int T, int B, int H, void* workspace,
+                float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
 size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
 
@@ -31,6 +31,7 @@ struct LstmSeqParams {
   long long ldw;
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
+  float* gates_seq;        // nullable [n_dir][T][B][4H] post-activation [g|i|f|o]; may alias pre
   int* counters;           // [n_dir][n_bt_total]
   int n_dir, T, B, H;
   int bt0;                 // first batch tile of this launch
@@ -79,7 +80,7 @@ lstm_seq_kernel(LstmSeqParams p) {
       const int to = dir ? T - 1 - s : s;
       const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) dst[g] = __ldg(q + g * H);
+      for (int g = 0; g < 4; ++g) dst[g] = __ldcg(q + g * H);
     }
   };
   load_pre(0, pre_next);
@@ -137,6 +138,10 @@ lstm_seq_kernel(LstmSeqParams p) {
       const float h = og * tanhf(c);
       __stcg(p.out + ((size_t)b * T + to) * outw + dir * H + unit, h);
       if (p.cell_seq) p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit] = c;
+      if (p.gates_seq) {
+        float* gs = p.gates_seq + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+        gs[0] = g; gs[H] = ig; gs[2 * H] = fg; gs[3 * H] = og;
+      }
     }
     __syncthreads();   // all h_s stores of this CTA issued; hs free for the next step
     if (tid == 0) {
@@ -160,7 +165,7 @@ extern "C" size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H) {
 }
 
 extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
-                                  float* out, float* cell_seq, int n_dir, int T, int B, int H,
+                                  float* out, float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H,
                                   void* workspace, size_t workspace_bytes, int backend,
                                   void* stream) {
   DANET_REQUIRE(pre && host_Wh && out && workspace, DANET_E_ARG, "lstm_seq: null pointer");
@@ -176,7 +181,7 @@ extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh,
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
   if (backend == 1)
-    return lstm_tc_fwd(pre, host_Wh, ldw, out, cell_seq, n_dir, T, B, H, workspace, workspace_bytes, st);
+    return lstm_tc_fwd(pre, host_Wh, ldw, out, cell_seq, gates_seq, n_dir, T, B, H, workspace, workspace_bytes, st);
 
   const size_t smem = lstm_smem_bytes(H);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: H %d needs %zu B of shared memory", H, smem);
@@ -198,6 +203,7 @@ extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh,
   p.ldw = ldw;
   p.out = out;
   p.cell_seq = cell_seq;
+  p.gates_seq = gates_seq;
   p.counters = reinterpret_cast<int*>(workspace);
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
   p.n_bt_total = n_bt;

@@ -45,6 +45,7 @@ struct LstmTcParams {
   long long ldw;
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
+  float* gates_seq;        // nullable [n_dir][T][B][4H] post-activation [g|i|f|o]; may alias pre
   int n_dir, T, B, H;
   long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
 };
@@ -222,10 +223,10 @@ lstm_tc_kernel(const LstmTcParams p) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (UPT == 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(q + g * H));
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(q + g * H));
             pre_next[g][0] = v.x; pre_next[g][1] = v.y; pre_next[g][UPT - 2] = v.z; pre_next[g][UPT - 1] = v.w;
           } else {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(q + g * H));
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(q + g * H));
             pre_next[g][0] = v.x; pre_next[g][1] = v.y;
           }
         }
@@ -270,6 +271,7 @@ lstm_tc_kernel(const LstmTcParams p) {
         const float ig = fast_sigmoid(a[uu][1]), fg = fast_sigmoid(a[uu][2]), og = fast_sigmoid(a[uu][3]);
         c[uu] = ig * gg + fg * c[uu];
         h[uu] = valid ? og * fast_tanh(c[uu]) : 0.f;
+        a[uu][1] = ig; a[uu][2] = fg; a[uu][3] = og;           // post-activation gates, kept for training
       }
       DANET_PROF(7);
       if (s < T - 1) {
@@ -291,6 +293,14 @@ lstm_tc_kernel(const LstmTcParams p) {
         // hand the staged slice to the sender warps (producer side of named barrier 1: no wait)
         asm volatile("bar.arrive 1, %0;" ::"r"(kEpiThreads + 32 * ncta) : "memory");
         DANET_PROF(8);
+      }
+      if (valid && p.gates_seq) {
+        float* gs = p.gates_seq + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (UPT == 4) *reinterpret_cast<float4*>(gs + g * H) = make_float4(a[0][g], a[1][g], a[UPT - 2][g], a[UPT - 1][g]);
+          else *reinterpret_cast<float2*>(gs + g * H) = make_float2(a[0][g], a[1][g]);
+        }
       }
       if (valid) {
         float* o = p.out + ((size_t)b * T + to) * outw + dir * H + unit;
@@ -360,7 +370,7 @@ size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
 bool lstm_tc_supported(int H) { return H % 4 == 0 && (H + kUnits - 1) / kUnits <= kMaxCta; }
 
 int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
-                int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                float* gates_seq, int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
@@ -376,7 +386,7 @@ int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, fl
   p.pre = pre;
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
-  p.ldw = ldw; p.out = out; p.cell_seq = cell_seq;
+  p.ldw = ldw; p.out = out; p.cell_seq = cell_seq; p.gates_seq = gates_seq;
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.

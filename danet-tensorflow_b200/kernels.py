@@ -195,10 +195,11 @@ def _req_strided(t, name):
     return t
 
 
-def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False):
+def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_gates=False):
     """
     pre [n_dir,T,B,4H]; w_list = the reference's stacked [I+H,4H] matrices, one per direction
-    (recurrent rows start at `in_dim`) -> hidden [B,T,n_dir*H] (+ cell [n_dir,T,B,H])
+    (recurrent rows start at `in_dim`) -> hidden [B,T,n_dir*H] (+ cell [n_dir,T,B,H]).
+    keep_gates: the post-activation gates [g|i|f|o] overwrite `pre` in place (training).
     [main.py:76-132; app/ops.py:139-147; app/modules.py:120-137]
     """
     pre = _req(pre, 'pre', dim=4)
@@ -223,7 +224,8 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False):
         be = DEFAULT_BACKEND if H <= TC_LSTM_MAX_H else 0
     else:
         be = backend
-    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), ptrs, 4 * H, _p(out), _p(cell), n_dir, T, B, H, _p(ws),
+    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), ptrs, 4 * H, _p(out), _p(cell), _p(pre) if keep_gates else None,
+                                      n_dir, T, B, H, _p(ws),
                                       ws.numel(), be, _stream()), 'lstm_seq')
     _count()
     return (out, cell) if keep_cell else out
@@ -417,3 +419,55 @@ def head_bwd(embed, attractors, mix, src, perm_idx, kind, est_mode, src_pwr=None
                'head_bwd_embed')
     _count(4)
     return {'d_embed': d_embed, 'd_attractors': d_attr, 'd_anchors': d_anchors}
+
+
+def lstm_seq_bwd(d_out, gates, cell, w_list, in_dim, T, B, H):
+    """
+    Backward through time [TF autodiff of main.py:125-131]: d_out [B,T,n_dir*H], gates [n_dir,T,B,4H]
+    (post-activation, from lstm_seq(keep_gates=True)) are overwritten IN PLACE with the pre-activation
+    gradients da; returns `gates` (now da).
+    """
+    d_out = _req(d_out, 'd_out', dim=3)
+    gates = _req(gates, 'gates', dim=4)
+    cell = _req(cell, 'cell', dim=4)
+    n_dir = len(w_list)
+    if tuple(gates.shape) != (n_dir, T, B, 4 * H) or tuple(cell.shape) != (n_dir, T, B, H) or \
+            tuple(d_out.shape) != (B, T, n_dir * H):
+        raise ValueError('lstm_seq_bwd: shapes %s %s %s' % (tuple(d_out.shape), tuple(gates.shape), tuple(cell.shape)))
+    ptrs = (C.c_void_p * n_dir)()
+    for d, w in enumerate(w_list):
+        w = _req(w, 'W[%d]' % d, dim=2)
+        ptrs[d] = w.data_ptr() + in_dim * 4 * H * 4
+    lib = _lib.load()
+    ws = _ws(lib.danet_lstm_seq_bwd_workspace_bytes(n_dir, B, H), gates.device)
+    _lib.check(lib.danet_lstm_seq_bwd(_p(d_out), _p(gates), _p(cell), ptrs, 4 * H, n_dir, T, B, H, _p(ws), ws.numel(),
+                                      _stream()), 'lstm_seq_bwd')
+    _count(2)
+    return gates
+
+
+def colsum(x, out=None, accumulate=False):
+    """column sums of a 2-D tensor (bias gradients)"""
+    x = _req_strided(x, 'x')
+    rows, n = x.shape
+    if out is None:
+        out = torch.empty((n,), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    ws = _ws(lib.danet_colsum_workspace_bytes(n), x.device)
+    _lib.check(lib.danet_colsum(_p(x), x.stride(0), rows, n, _p(out), int(accumulate), _p(ws), ws.numel(), _stream()),
+               'colsum')
+    _count(2)
+    return out
+
+
+def clip_adam(param, grad, m, v, step, lr=3e-4, clip=100., beta1=.9, beta2=.999, eps=1e-8, grad_scale=1.):
+    """in place: clip_by_value then Adam [main.py:359-363; app/ozers.py:15-18]"""
+    for t, nm in ((param, 'param'), (grad, 'grad'), (m, 'm'), (v, 'v')):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError('clip_adam: %s must be a contiguous float32 CUDA tensor' % nm)
+        if t.numel() != param.numel():
+            raise ValueError('clip_adam: %s has %d elements, param %d' % (nm, t.numel(), param.numel()))
+    _lib.check(_lib.load().danet_clip_adam(_p(param), _p(grad), _p(m), _p(v), param.numel(), grad_scale,
+                                           clip if clip is not None else 0., lr, beta1, beta2, eps, int(step),
+                                           _stream()), 'clip_adam')
+    _count()

@@ -32,6 +32,9 @@ class Model(object):
         self._stagger_event = None
         self._streams = []
         self._graphs = {}
+        self._tape = None                 # training: saved activations per recurrent layer
+        self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
+        self.step_count = 0
 
     # ---------------------------------------------------------------- variables
     def get_variable(self, name, shape, init):
@@ -52,7 +55,11 @@ class Model(object):
         """Take weights by reference name (numpy arrays or tensors); the role of main.py:201-206"""
         for k, v in params.items():
             t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
-            self.params[k] = t.to(device=self.device, dtype=torch.float32).contiguous()
+            t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            if self._flat is not None and k in self.params:
+                self.params[k].copy_(t)          # keep the flat-buffer views
+            else:
+                self.params[k] = t
 
     def save_params(self, path):
         """main.py:192-199 -- trainable variables only (no optimiser slots)"""
@@ -77,6 +84,10 @@ class Model(object):
         pre = K.linear(x2, W, Bv, time_major_T=T, k_rows=I).view(1, T, B, 4 * hdim)
         if reverse:
             raise NotImplementedError('single reversed direction: use lyr_bilstm')
+        if self._tape is not None:
+            out, cell = K.lstm_seq(pre, [W], I, T, B, hdim, keep_cell=True, keep_gates=True)
+            self._tape.append(dict(name=name, x=s_x, gates=pre, cell=cell, out=out, hdim=hdim))
+            return out
         return K.lstm_seq(pre, [W], I, T, B, hdim)
 
     def lyr_bilstm(self, name, s_x, hdim, w_init=None, b_init=None):
@@ -84,6 +95,8 @@ class Model(object):
         B, T, I = s_x.shape
         Wf, Bf = self._lstm_vars(name + '_fwd', I, hdim, w_init, b_init)
         Wb, Bb = self._lstm_vars(name + '_bwd', I, hdim, w_init, b_init)
+        if self._tape is not None:
+            return self._lyr_bilstm_train(name, s_x, hdim, (Wf, Bf, Wb, Bb))
         x2 = s_x.reshape(B * T, I)
         pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
         K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
@@ -92,6 +105,130 @@ class Model(object):
             self._stagger_pending = False
             self._stagger_event = torch.cuda.current_stream().record_event()
         return K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
+
+    # ---------------------------------------------------------------- training step (row a16)
+    def _lyr_bilstm_train(self, name, s_x, hdim, weights):
+        Wf, Bf, Wb, Bb = weights
+        B, T, I = s_x.shape
+        x2 = s_x.reshape(B * T, I)
+        pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
+        K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
+        K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))
+        out, cell = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True)
+        self._tape.append(dict(name=name, x=s_x, gates=pre, cell=cell, out=out, hdim=hdim))
+        return out
+
+    def flatten_params(self):
+        """Re-home every variable in ONE flat buffer (views keep the reference names), with matching flat
+        gradient and Adam-moment buffers: the gradient all-reduce and the clip+Adam update are then one
+        call each over ~9 M floats."""
+        names = list(self.params)
+        offs, total = {}, 0
+        for k in names:
+            offs[k] = total
+            total += (self.params[k].numel() + 63) // 64 * 64          # 256-byte aligned views
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        grad = torch.zeros_like(flat)
+        for k in names:
+            v = self.params[k]
+            view = flat[offs[k]:offs[k] + v.numel()].view(v.shape)
+            view.copy_(v)
+            self.params[k] = view
+        self._flat = dict(param=flat, grad=grad, m=torch.zeros_like(flat), v=torch.zeros_like(flat), offs=offs)
+        self.grads = {k: grad[offs[k]:offs[k] + self.params[k].numel()].view(self.params[k].shape) for k in names}
+        return self._flat
+
+    def train_forward_backward(self, src):
+        """One forward + backward of the train loss (main.py:289, 357-358) on complex spectra src [B,C,T,F];
+        fills self.grads (views of one flat buffer), returns dict(loss, snr).  No optimiser step."""
+        if self.estimator is None:
+            self.build()
+        if self._flat is None:
+            self.reset()
+            self.flatten_params()
+        est_name = hparams.TRAIN_ESTIMATOR_METHOD
+        if est_name not in ('anchor', 'truth', 'truth-threshold', 'truth-weighted'):
+            raise NotImplementedError('no backward for estimator %r' % est_name)
+        src = src.to(self.device)
+        B, Cn, T, F = src.shape
+        E = hparams.EMBED_SIZE
+        feats = K.mix_features(src)
+        # ---- forward, recording what the backward needs
+        enc = self.encoder
+        n_layers, hdim = enc._geometry()
+        self._tape = []
+        try:
+            embed = enc(feats['logmag'])
+        finally:
+            tape, self._tape = self._tape, None
+        xc = self._last_centered                                      # input of the output projection
+        embed_flat = embed.view(B, T * F, E)
+        if est_name == 'anchor':
+            anchors = self.estimator.anchors()
+            attrs, _, _, choice, den = K.attractor_anchor(embed, anchors, Cn, return_den=True)
+        else:
+            anchors, choice = None, None
+            attrs, den = K.attractor_truth(embed, feats['src_pwr'], feats['mix_pwr'], est_name, return_den=True)
+        sep = K.mask_cmul(embed_flat, attrs, feats['mix'], hparams.SEPARATOR_TYPE, want=('sep',))['sep']
+        pit = K.pit_mse(src, sep)
+        # ---- backward
+        grads = self.grads
+        g = K.head_bwd(embed, attrs, feats['mix'], src, pit['perm_idx'], hparams.SEPARATOR_TYPE, est_name,
+                       src_pwr=feats['src_pwr'], mix_pwr=feats['mix_pwr'], anchors=anchors, choice=choice, den=den)
+        if est_name == 'anchor':
+            grads[self.estimator.name + '/anchors'].copy_(g['d_anchors'])
+        dV = g['d_embed'].view(B * T, F * E)
+        Wout = self.params[enc.name + '/output/W']
+        K.gemm(xc.view(B * T, -1), dV, trans_a=True, out=grads[enc.name + '/output/W'])     # dW = X^T dY
+        dx = K.gemm(dV, Wout, trans_b=True)                                                 # dX = dY W^T
+        dx = K.center(dx.view(B, T, -1))                      # gradient of x - mean(x) is the same centring
+        for l in range(n_layers - 1, -1, -1):
+            rec = tape[l]
+            H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
+            names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if enc.BIDIR else [rec['name']]
+            Ws = [self.params[n + '/LSTM/linear/W'] for n in names]
+            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)              # [n_dir,T,B,4H]
+            x2 = x.reshape(B * T, I)
+            out2 = rec['out'].view(B * T, -1)
+            dx_prev = torch.empty((B * T, I), dtype=torch.float32, device=src.device) if l > 0 else None
+            for d, n in enumerate(names):
+                da_d = da[d].view(T * B, 4 * H)
+                dW = grads[n + '/LSTM/linear/W']
+                K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                      # dWx = sum X[b,t]^T da[t,b]
+                K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,          # dWh = sum h[b,t-+1]^T da[t,b]
+                       shift_a=-1 if d == 0 else 1, out=dW[I:])
+                K.colsum(da_d, out=grads[n + '/LSTM/linear/B'])
+                if l > 0:
+                    K.gemm(da_d, Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
+            if l > 0:
+                dx = dx_prev.view(B, T, I)
+        return dict(loss=pit['loss'][0], snr=pit['snr'].mean(), perm_idx=pit['perm_idx'])
+
+    def all_reduce_grads(self):
+        """the ONE collective of the system (SURVEY.md 8e): sum of the flat gradient buffer over ranks;
+        the mean is folded into the Adam kernel's grad_scale"""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self._flat['grad'])
+            return 1. / dist.get_world_size()
+        return 1.
+
+    def apply_gradients(self, grad_scale=1.):
+        """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then Adam, one fused launch over all variables"""
+        self.step_count += 1
+        f = self._flat
+        K.clip_adam(f['param'], f['grad'], f['m'], f['v'], self.step_count, lr=hparams.LR,
+                    clip=hparams.GRAD_CLIP_THRES)
+
+    def train_step(self, src):
+        """train fetches (main.py:369-375): forward, backward, gradient all-reduce, clip + Adam"""
+        out = self.train_forward_backward(src)
+        scale = self.all_reduce_grads()
+        self.step_count += 1
+        f = self._flat
+        K.clip_adam(f['param'], f['grad'], f['m'], f['v'], self.step_count, lr=hparams.LR,
+                    clip=hparams.GRAD_CLIP_THRES, grad_scale=scale)
+        return out
 
     # ---------------------------------------------------------------- assembly
     def build(self):

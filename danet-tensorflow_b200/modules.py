@@ -99,6 +99,7 @@ class _RecurrentEncoder(Encoder):
             else:
                 x = model.lyr_lstm('%s/lstm%d' % (self.name, l), x, hdim, w_init=w_init, b_init=b_init)
         x = K.center(x)                                            # modules.py:244-245 / :181-182
+        model._last_centered = x
         odim = x.shape[-1]
         E = hparams.EMBED_SIZE
         W = model.get_variable('%s/output/W' % self.name, [odim, F * E], _uniform(-1.85, 1.85))

@@ -107,11 +107,30 @@ int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shift
  *   Wh    n_dir pointers to the recurrent rows W[I:I+H, 0:4H] (row stride ldw)
  *   out   [B][T][n_dir*H]  hidden sequence, fwd in [0,H), bwd in [H,2H) (un-reversed)
  *   cell_seq (nullable) [n_dir][T][B][H] cell states kept for the backward pass
+ *   gates_seq (nullable) [n_dir][T][B][4H] post-activation gates [g|i|f|o] kept for the
+ *         backward pass; MAY ALIAS pre (each element is read once, then overwritten)
  * backend: 0 = fp32 SIMT cooperative kernel, 1 = tcgen05 cluster kernel. */
 size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H);
 int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
-                       float* out, float* cell_seq, int n_dir, int T, int B, int H,
+                       float* out, float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H,
                        void* workspace, size_t workspace_bytes, int backend, void* stream);
+/* backward through time (TF autodiff of the tf.scan at main.py:125-131): walks the sequence in
+ * reverse, dh = d_out_t + da_{t+1} Wh^T, and overwrites `gates` ([g|i|f|o] from the forward) with
+ * the pre-activation gradients da in place.  dWx / dWh / dX are danet_gemm calls on da;
+ * the bias gradient is danet_colsum.  Exact fp32 cooperative kernel. */
+size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H);
+int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
+                       const float* const* host_Wh, long long ldw, int n_dir, int T, int B, int H,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* out[n] (+)= sum over rows of x[rows, n] (row stride ld): bias gradients. workspace: 64*n floats */
+size_t danet_colsum_workspace_bytes(int n);
+int danet_colsum(const float* x, long long ld, long long rows, int n, float* out, int accumulate,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* a16: clip_by_value(+-clip) then TF1 AdamOptimizer (main.py:359-363, app/ozers.py:15-18):
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; theta -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies
+ * the gradient first (1/world_size after an all-reduce sum).  clip <= 0 disables clipping. */
+int danet_clip_adam(float* param, const float* grad, float* m, float* v, long long n, float grad_scale,
+                    float clip, float lr, float beta1, float beta2, float eps, int step, void* stream);
 
 /* ---- K3  attractor estimation ---------------------------------------------
  * truth family replaces app/modules.py:390-412 (mode 0: plain, denominator n+1),

@@ -450,3 +450,85 @@ def test_head_backward(K, kind, est, B, C, T, E):
     assert rel(g['d_embed'].view(B, T, 129, E), Vt.grad) < 2e-4
     if est == 'anchor':
         assert rel(g['d_anchors'], an.grad) < 2e-4
+
+
+# ---------------------------------------------------------------- training step (row a16)
+def test_lstm_layer_backward(K):
+    """BPTT kernel + dW/dX products of one BiLSTM layer against torch autograd on the oracle"""
+    rs = np.random.RandomState(11)
+    B, T, I, H = 3, 9, 40, 64
+    r = .75 / np.sqrt(H)
+    x = rs.standard_normal((B, T, I)).astype(np.float32)
+    Ws = [rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32) for _ in range(2)]
+    Bs = [(O.lstm_bias_init(H) + 0.1 * rs.standard_normal(4 * H)).astype(np.float32) for _ in range(2)]
+    dout = rs.standard_normal((B, T, 2 * H)).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    Wt = [torch.from_numpy(w).double().requires_grad_(True) for w in Ws]
+    Bt = [torch.from_numpy(b).double().requires_grad_(True) for b in Bs]
+    y = O.bilstm_layer(xt, Wt[0], Bt[0], Wt[1], Bt[1])
+    (y * torch.from_numpy(dout).double()).sum().backward()
+    # device
+    xg, Wg = cuda(x), [cuda(w) for w in Ws]
+    pre = torch.empty(2, T, B, 4 * H, device='cuda')
+    for d in range(2):
+        K.linear(xg.view(B * T, I), Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
+    for backend in (0, 1):
+        p = pre.clone()
+        out, cell = K.lstm_seq(p, Wg, I, T, B, H, backend=backend, keep_cell=True, keep_gates=True)
+        assert rel(out, y) < 1e-4
+        da = K.lstm_seq_bwd(cuda(dout), p, cell, Wg, I, T, B, H)
+        dx = torch.zeros(B * T, I, device='cuda')
+        for d in range(2):
+            da_d = da[d].view(T * B, 4 * H)
+            dWx = K.gemm(xg.view(B * T, I), da_d, trans_a=True, perm_a_T=T)
+            dWh = K.gemm(out.view(B * T, 2 * H)[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,
+                         shift_a=-1 if d == 0 else 1)
+            db = K.colsum(da_d)
+            K.gemm(da_d, Wg[d][:I], trans_b=True, out_perm_T=B, out=dx, accumulate=d > 0)
+            assert rel(torch.cat([dWx, dWh], 0), Wt[d].grad) < 2e-4
+            assert rel(db, Bt[d].grad) < 2e-4
+        assert rel(dx.view(B, T, I), xt.grad) < 2e-4
+
+
+def test_clip_adam(K):
+    rs = np.random.RandomState(4)
+    n = 100003
+    p0, g0 = rs.standard_normal(n).astype(np.float32), (rs.standard_normal(n) * 80).astype(np.float32)
+    params, grads = {'w': torch.from_numpy(p0).double()}, {'w': torch.from_numpy(g0).double()}
+    m, v = {'w': torch.zeros(n, dtype=torch.float64)}, {'w': torch.zeros(n, dtype=torch.float64)}
+    pg, mg, vg = cuda(p0), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    for step in (1, 2, 3):
+        O.clip_adam_step(params, grads, m, v, step)
+        K.clip_adam(pg, cuda(g0), mg, vg, step)
+    assert rel(pg, params['w']) < 1e-6
+    assert float((cuda(g0).abs() > 100).float().mean()) > 0.1        # the clip was exercised
+
+
+GRAD_FILES = [p for p in MODEL_FILES if 'lstm_tw' not in os.path.basename(p) or 'bilstm' in os.path.basename(p)]
+
+
+@pytest.mark.parametrize('path', MODEL_FILES, ids=[os.path.basename(p)[6:-4] for p in MODEL_FILES])
+def test_model_gradients_golden(D, path):
+    """gradients of the train loss against the values the REFERENCE's own graph produced (tf.gradients under
+    the eager shim; fixtures store the L2 norm and sampled entries of selected variables) + one Adam step"""
+    d, meta, over, P = _load_case(path)
+    hp = D.Hyperparameter()
+    hp.load({k: v for k, v in over.items() if k not in ('FLOATX', 'DEBUG')})
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(hp.__dict__)
+    D.hparams.digest()
+    D.kernels.DEFAULT_BACKEND = 1
+    model = D.Model('grad').build()
+    model.load_params(P)
+    model.reset()
+    model.flatten_params()
+    out = model.train_forward_backward(cuda(d['src'].astype(np.complex64)))
+    assert abs(float(out['loss']) - float(d['train_loss'])) <= TOL * abs(float(d['train_loss']))
+    for n in meta['grad_names']:
+        key = n.replace('/', '.').replace(':0', '')
+        g = model.grads[n.replace('global/', '').replace(':0', '')].cpu().numpy().astype(np.float64)
+        ref_l2 = float(d['grad_l2.' + key])
+        assert abs(np.sqrt((g * g).sum()) - ref_l2) <= TOL * max(ref_l2, 1e-30), n
+        got = g.reshape(-1)[d['grad_idx.' + key]]
+        ref = d['grad_val.' + key]
+        assert np.abs(got - ref).max() <= TOL * max(np.abs(ref).max(), 1e-30) + 1e-6 * ref_l2, n

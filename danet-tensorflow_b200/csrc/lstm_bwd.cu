@@ -14,8 +14,6 @@
 
 namespace danet {
 
-constexpr int kBU = 16;     // hidden units per CTA
-constexpr int kBB = 16;     // utterances per CTA
 constexpr int kKS = 4;      // split of the 4H reduction across lanes
 
 __device__ __forceinline__ int ld_acquire_i(const int* p) {
@@ -32,21 +30,26 @@ struct LstmBwdParams {
   long long ldw;
   int* counters;           // [n_dir][n_bt]
   int n_dir, T, B, H, bt0, n_bt_total;
+  int ldd;                 // row stride (floats) of the shared da tile, padded against bank conflicts
 };
 
-__global__ void __launch_bounds__(256)
+// kBU hidden units x kBB utterances per CTA (16 x 16 for H <= 320; 8 x 8 when 4H rows no longer fit)
+template <int kBU, int kBB>
+__global__ void __launch_bounds__((kBU / 2) * (kBB / 2) * kKS)
 lstm_bwd_kernel(LstmBwdParams p) {
+  constexpr int NT = (kBU / 2) * (kBB / 2) * kKS;
   extern __shared__ __align__(16) float smem[];
   const int H = p.H, T = p.T, B = p.B, G4 = 4 * H;
   float* sW = smem;                        // [kBU][4H]
-  float* sD = sW + (size_t)kBU * G4;       // [kBB][4H]  da_{t+1} of this batch tile
-  const int tid = threadIdx.x, lane = tid & 31;
+  float* sD = sW + (size_t)kBU * G4;       // [kBB][ldd]  da_{t+1} of this batch tile
+  const int ldd = p.ldd;
+  const int tid = threadIdx.x;
   const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
   const int n_chunks = gridDim.x;
   const int u0 = chunk * kBU, b0 = bt * kBB;
 
   const float* Wg = p.Wh[dir];
-  for (int i = tid; i < kBU * (G4 / 4); i += 256) {
+  for (int i = tid; i < kBU * (G4 / 4); i += NT) {
     const int u = i / (G4 / 4), q = i % (G4 / 4);
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (u0 + u < H) w = __ldg(reinterpret_cast<const float4*>(Wg + (size_t)(u0 + u) * p.ldw) + q);
@@ -54,7 +57,7 @@ lstm_bwd_kernel(LstmBwdParams p) {
   }
   // thread -> 2 utterances x 2 units, one quarter of the 4H reduction; 64 tiles x 4 quarters
   const int ks = tid & (kKS - 1), tile = tid >> 2;
-  const int tb = (tile & 7) * 2, tu = (tile >> 3) * 2;          // local utterance / unit of the 2x2 tile
+  const int tb = (tile % (kBB / 2)) * 2, tu = (tile / (kBB / 2)) * 2;   // local utterance / unit of the 2x2 tile
   const int kq = (G4 / 4 + kKS - 1) / kKS;                      // float4 per quarter (ceil)
   const int q_lo = ks * kq, q_hi = min(G4 / 4, q_lo + kq);
   int* counter = p.counters + dir * p.n_bt_total + bt;
@@ -66,6 +69,24 @@ lstm_bwd_kernel(LstmBwdParams p) {
 
   for (int s = T - 1; s >= 0; --s) {       // processing index; original time of this step:
     const int to = dir ? T - 1 - s : s;
+    const int tp = dir ? to + 1 : to - 1;  // original time of the previously processed state c_{t-1}
+    // everything that does not depend on the recurrence is fetched BEFORE waiting for da_{s+1}
+    float gg[2][2], ig[2][2], fg[2][2], og[2][2], cc[2][2], cp[2][2], dout[2][2];
+    if (ks == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int b = b0 + tb + i, unit = u0 + tu + j;
+          const bool ok = b < B && unit < H;
+          const float* gt = p.gates + (((size_t)dir * T + to) * B + (ok ? b : 0)) * G4 + (ok ? unit : 0);
+          gg[i][j] = __ldcg(gt); ig[i][j] = __ldcg(gt + H); fg[i][j] = __ldcg(gt + 2 * H); og[i][j] = __ldcg(gt + 3 * H);
+          const size_t ci = ((size_t)dir * T * B + (ok ? b : 0)) * H + (ok ? unit : 0);
+          cc[i][j] = __ldg(p.cell_seq + ci + (size_t)to * B * H);
+          cp[i][j] = s > 0 ? __ldg(p.cell_seq + ci + (size_t)tp * B * H) : 0.f;
+          dout[i][j] = __ldg(p.d_out + ((size_t)(ok ? b : 0) * T + to) * outw + dir * H + (ok ? unit : 0));
+        }
+    }
     float dh[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     if (s < T - 1) {
       // da of processing step s+1 (original time tn) from every CTA of the group
@@ -75,16 +96,29 @@ lstm_bwd_kernel(LstmBwdParams p) {
         while (ld_acquire_i(counter) < want) {}
       }
       __syncthreads();
-      for (int i = tid; i < kBB * (G4 / 4); i += 256) {
-        const int r = i / (G4 / 4), q = i % (G4 / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b0 + r < B)
-          v = __ldcg(reinterpret_cast<const float4*>(p.gates + (((size_t)dir * T + tn) * B + b0 + r) * G4) + q);
-        reinterpret_cast<float4*>(sD)[i] = v;
+      {
+        constexpr int kUnroll = 4;
+        const int nq = G4 / 4, total = kBB * nq;
+        const float4* src = reinterpret_cast<const float4*>(p.gates + (((size_t)dir * T + tn) * B + b0) * G4);
+        const int rows_ok = min(kBB, B - b0);
+        for (int i0 = tid; i0 < total; i0 += NT * kUnroll) {
+          float4 v[kUnroll];
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int i = i0 + k * NT;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < total && i / nq < rows_ok) v[k] = __ldcg(src + i);     // rows of one time step are contiguous
+          }
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int i = i0 + k * NT;
+            if (i < total) *reinterpret_cast<float4*>(sD + (size_t)(i / nq) * ldd + 4 * (i % nq)) = v[k];
+          }
+        }
       }
       __syncthreads();
-      const float4* d0 = reinterpret_cast<const float4*>(sD + (size_t)tb * G4);
-      const float4* d1 = reinterpret_cast<const float4*>(sD + (size_t)(tb + 1) * G4);
+      const float4* d0 = reinterpret_cast<const float4*>(sD + (size_t)tb * ldd);
+      const float4* d1 = reinterpret_cast<const float4*>(sD + (size_t)(tb + 1) * ldd);
       const float4* w0 = reinterpret_cast<const float4*>(sW + (size_t)tu * G4);
       const float4* w1 = reinterpret_cast<const float4*>(sW + (size_t)(tu + 1) * G4);
 #pragma unroll 2
@@ -108,7 +142,6 @@ lstm_bwd_kernel(LstmBwdParams p) {
         }
     }
     if (ks == 0) {
-      const int tp = dir ? to + 1 : to - 1;          // original time of the PREVIOUS processed state c_{t-1}
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -116,17 +149,14 @@ lstm_bwd_kernel(LstmBwdParams p) {
           const int b = b0 + tb + i, unit = u0 + tu + j;
           if (b < B && unit < H) {
             float* gt = p.gates + (((size_t)dir * T + to) * B + b) * G4 + unit;
-            const float gg = gt[0], ig = gt[H], fg = gt[2 * H], og = gt[3 * H];
-            const float c = p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit];
-            const float cp = s > 0 ? p.cell_seq[(((size_t)dir * T + tp) * B + b) * H + unit] : 0.f;
-            const float dht = dh[i][j] + p.d_out[((size_t)b * T + to) * outw + dir * H + unit];
-            const float th = tanhf(c);
-            const float dc = dht * og * (1.f - th * th) + dc_next[i][j];
-            dc_next[i][j] = dc * fg;
-            __stcg(gt, dc * ig);                                  // da_g (candidate has no tanh)
-            __stcg(gt + H, dc * gg * ig * (1.f - ig));            // da_i
-            __stcg(gt + 2 * H, dc * cp * fg * (1.f - fg));        // da_f
-            __stcg(gt + 3 * H, dht * th * og * (1.f - og));       // da_o
+            const float dht = dh[i][j] + dout[i][j];
+            const float th = tanhf(cc[i][j]);
+            const float dc = dht * og[i][j] * (1.f - th * th) + dc_next[i][j];
+            dc_next[i][j] = dc * fg[i][j];
+            __stcg(gt, dc * ig[i][j]);                                              // da_g (candidate has no tanh)
+            __stcg(gt + H, dc * gg[i][j] * ig[i][j] * (1.f - ig[i][j]));            // da_i
+            __stcg(gt + 2 * H, dc * cp[i][j] * fg[i][j] * (1.f - fg[i][j]));        // da_f
+            __stcg(gt + 3 * H, dht * th * og[i][j] * (1.f - og[i][j]));             // da_o
           }
         }
     }
@@ -138,7 +168,47 @@ lstm_bwd_kernel(LstmBwdParams p) {
   }
 }
 
-static size_t lstm_bwd_smem_bytes(int H) { return (size_t)(kBU + kBB) * 4 * H * sizeof(float); }
+template <int kBU, int kBB>
+static int launch_lstm_bwd(LstmBwdParams p, cudaStream_t st) {
+  constexpr int NT = (kBU / 2) * (kBB / 2) * kKS;
+  const int H = p.H, B = p.B, n_dir = p.n_dir;
+  // pad the da rows so the 8 lanes of a quarter warp (4 reduction quarters x 2 utterance pairs) hit
+  // distinct 16-byte bank groups: without it the 16 x 4H tile serialises 8-way on every LDS.128
+  {
+    const int q4 = 4 * H / 4, kq = (q4 + kKS - 1) / kKS;
+    int best_pad = 0, best = -1;
+    for (int pad = 0; pad < 8; ++pad) {
+      unsigned seen = 0;
+      for (int t = 0; t < 2; ++t)
+        for (int ks = 0; ks < kKS; ++ks) seen |= 1u << ((ks * kq + t * 2 * (q4 + pad)) & 7);
+      const int distinct = __builtin_popcount(seen);
+      if (distinct > best) { best = distinct; best_pad = pad; }
+    }
+    p.ldd = 4 * (q4 + best_pad);
+  }
+  const size_t smem = ((size_t)kBU * 4 * H + (size_t)kBB * p.ldd) * sizeof(float);
+  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq_bwd: H %d needs %zu B of shared memory", H, smem);
+  DANET_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<kBU, kBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel<kBU, kBB>, NT, smem));
+  const int n_chunks = (H + kBU - 1) / kBU;
+  const int n_bt = (B + kBB - 1) / kBB;
+  const int resident = per_sm * num_sms();
+  int bt_per_launch = resident / (n_dir * n_chunks);
+  DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE, "lstm_seq_bwd: one batch tile needs %d resident CTAs, device holds %d",
+                n_dir * n_chunks, resident);
+  if (bt_per_launch > n_bt) bt_per_launch = n_bt;
+  DANET_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)n_dir * n_bt * sizeof(int), st));
+  p.n_bt_total = n_bt;
+  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
+    p.bt0 = bt0;
+    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
+    void* args[] = {&p};
+    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<kBU, kBB>, dim3(n_chunks, nb, n_dir), dim3(NT),
+                                           args, smem, st));
+  }
+  return DANET_OK;
+}
 
 }  // namespace danet
 
@@ -147,7 +217,7 @@ using namespace danet;
 extern "C" size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H) {
   (void)H;
   if (n_dir < 1 || B < 1) return 256;
-  return (((size_t)n_dir * ((B + kBB - 1) / kBB) * sizeof(int)) + 255) / 256 * 256;
+  return (((size_t)n_dir * ((B + 7) / 8) * sizeof(int)) + 255) / 256 * 256;
 }
 
 extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
@@ -163,32 +233,12 @@ extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float*
                 "lstm_seq_bwd: workspace too small");
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
-  const size_t smem = lstm_bwd_smem_bytes(H);
-  DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq_bwd: H %d needs %zu B of shared memory", H, smem);
-  DANET_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel, 256, smem));
-  const int n_chunks = (H + kBU - 1) / kBU;
-  const int n_bt = (B + kBB - 1) / kBB;
-  const int resident = per_sm * num_sms();
-  int bt_per_launch = resident / (n_dir * n_chunks);
-  DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE, "lstm_seq_bwd: one batch tile needs %d resident CTAs, device holds %d",
-                n_dir * n_chunks, resident);
-  if (bt_per_launch > n_bt) bt_per_launch = n_bt;
-  DANET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_dir * n_bt * sizeof(int), st));
   LstmBwdParams p;
   p.d_out = d_out; p.gates = gates; p.cell_seq = cell_seq;
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
   p.ldw = ldw;
   p.counters = reinterpret_cast<int*>(workspace);
-  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.n_bt_total = n_bt;
-  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
-    p.bt0 = bt0;
-    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
-    void* args[] = {&p};
-    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel, dim3(n_chunks, nb, n_dir), dim3(256), args,
-                                           smem, st));
-  }
-  return DANET_OK;
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.n_bt_total = 0; p.bt0 = 0;
+  return H <= 320 ? launch_lstm_bwd<16, 16>(p, st) : launch_lstm_bwd<8, 8>(p, st);
 }

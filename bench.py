@@ -42,18 +42,23 @@ N_LAYERS = 4
 def synth_mixtures(batch, n_samples, seed):
     """per source white noise through a one-pole low-pass (a = 0.9) x a 4 Hz
     raised-cosine envelope with random phase, RMS 1000 (int16 scale); mixture = sum of sources."""
+    return synth_sources(batch, n_samples, seed).sum(1).astype(np.float32)
+
+
+def synth_sources(batch, n_samples, seed):
+    """the per-source waveforms [B, C, N] behind synth_mixtures (training consumes the sources)"""
     rs = np.random.RandomState(seed)
     x = rs.standard_normal((batch, N_SPK, n_samples)).astype(np.float64)
     y = np.empty_like(x)
     acc = np.zeros((batch, N_SPK))
-    for i in range(n_samples):          # one-pole IIR; vectorised over (batch, source)
+    for i in range(n_samples):
         acc = 0.9 * acc + x[..., i]
         y[..., i] = acc
     t = np.arange(n_samples) / 8000.
     ph = rs.uniform(0, 2 * np.pi, (batch, N_SPK, 1))
     y *= 0.5 - 0.5 * np.cos(2 * np.pi * 4. * t + ph)
     y *= 1000. / np.sqrt((y ** 2).mean(-1, keepdims=True))
-    return y.sum(1).astype(np.float32)
+    return y.astype(np.float32)
 
 
 def reference_params(seed=1337):
@@ -174,6 +179,7 @@ def main():
     ap.add_argument('--cpu-baseline-mixtures', type=int, default=32)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1 = replay the step from a CUDA graph (default), 0 = eager')
+    ap.add_argument('--train-steps', type=int, default=3, help='timed training steps for the extra "train" key (0 = skip)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -271,6 +277,20 @@ def main():
     lstm_ms = [a.elapsed_time(b) for a, b in lstm_events]
     clocks = sampler.stop()
 
+    # ---- extra: the training step of the same config (forward + backward + gradient all-reduce + clip/Adam)
+    train = None
+    if args.train_steps > 0:
+        src = K.stft(torch.from_numpy(synth_sources(B, N_SAMPLES, 1337 + rank)).to(dev))     # [B,C,T,F] complex
+        for _ in range(2):
+            model.train_step(src)
+        K.launches = 0
+        ms_train = timed_loop(lambda: model.train_step(src), args.train_steps)
+        train = {'value': B * world * args.train_steps / (ms_train / 1e3), 'unit': 'mixtures/s',
+                 'ms_per_step': ms_train / args.train_steps, 'steps': args.train_steps,
+                 'gpu_launches': K.launches,
+                 'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (fp32 BPTT kernel + tcgen05 dW/dX products), '
+                         'one NCCL all-reduce of the flat gradient buffer (N > 1), fused clip + Adam'}
+
     total = B * world
     value = total * args.steps / (ms_dev / 1e3)
     e2e = total * args.steps / (ms_e2e / 1e3)
@@ -320,7 +340,7 @@ def main():
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
-        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph),
+        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -52,3 +52,27 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import danet_tensorflow_b200 as D
+    model = D.Model('ddp', device='cpu')
+    # the flat gradient buffer of a 2-variable model; rank r holds gradient (r + 1) everywhere
+    flat = torch.full((128,), float(rank + 1))
+    model._flat = dict(grad=flat)
+    scale = model.all_reduce_grads()
+    out[rank] = (flat.numpy().copy(), scale)
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_is_a_mean_over_ranks():
+    """the one collective of the training step: sum of the flat gradient buffer, 1/world folded into Adam"""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        g, scale = out[r]
+        assert np.all(g == 3.) and scale == 0.5          # (1 + 2) summed; mean = 1.5 after the scale

@@ -33,7 +33,7 @@ PROTOTYPES = {
     'danet_lstm_seq_fwd': (c_i, [c_f, C.POINTER(C.c_void_p), c_ll, c_f, c_f, c_f, c_i, c_i, c_i, c_i,
                                  c_v, c_sz, c_i, c_v]),
     'danet_lstm_seq_bwd_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
-    'danet_lstm_seq_bwd': (c_i, [c_f, c_f, c_f, C.POINTER(C.c_void_p), c_ll, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
+    'danet_lstm_seq_bwd': (c_i, [c_f, c_f, c_f, C.POINTER(C.c_void_p), c_ll, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
     'danet_colsum_workspace_bytes': (c_sz, [c_i]),
     'danet_colsum': (c_i, [c_f, c_ll, c_ll, c_i, c_f, c_i, c_v, c_sz, c_v]),
     'danet_clip_adam': (c_i, [c_f, c_f, c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -9,10 +9,13 @@
 // (the dW = X^T da / dX = da W^T products are danet_gemm calls on that buffer).
 // Exact fp32, persistent cooperative kernel: a CTA owns 16 hidden units x 16 utterances of one direction,
 // keeps its 16 rows of Wh (16 x 4H) in shared memory, and per step pulls the group's da_{t+1} [16 x 4H]
-// through L2 (release/acquire counter, as lstm.cu).  A tcgen05 cluster version is the next step.
+// through L2 (release/acquire counter, as lstm.cu).  backend 1 is the tcgen05 cluster kernel (lstm_bwd_tc.cu).
 #include "common.cuh"
 
 namespace danet {
+
+int lstm_bwd_tc(const float* d_out, float* gates, const float* cell_seq, const float* const* host_Wh, long long ldw,
+                int n_dir, int T, int B, int H, cudaStream_t stream);
 
 constexpr int kKS = 4;      // split of the 4H reduction across lanes
 
@@ -222,7 +225,7 @@ extern "C" size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H) {
 
 extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
                                   const float* const* host_Wh, long long ldw, int n_dir, int T, int B, int H,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  void* workspace, size_t workspace_bytes, int backend, void* stream) {
   DANET_REQUIRE(d_out && gates && cell_seq && host_Wh && workspace, DANET_E_ARG, "lstm_seq_bwd: null pointer");
   DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_seq_bwd: n_dir %d", n_dir);
   for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_seq_bwd: null Wh[%d]", d);
@@ -231,8 +234,10 @@ extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float*
   DANET_REQUIRE(aligned16(gates) && aligned16(host_Wh[0]), DANET_E_ALIGN, "lstm_seq_bwd: gates / Wh must be 16-byte aligned");
   DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_bwd_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
                 "lstm_seq_bwd: workspace too small");
+  DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq_bwd: backend %d", backend);
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
+  if (backend == 1) return lstm_bwd_tc(d_out, gates, cell_seq, host_Wh, ldw, n_dir, T, B, H, st);
   LstmBwdParams p;
   p.d_out = d_out; p.gates = gates; p.cell_seq = cell_seq;
   p.Wh[0] = host_Wh[0];

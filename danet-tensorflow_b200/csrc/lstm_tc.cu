@@ -56,40 +56,6 @@ constexpr int kProfSlots = 16;
     if (prof_on) p.prof[(size_t)s * kProfSlots + (slot)] = clock64();                      \
   } while (0)
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// local shared -> a peer CTA's shared memory, completion counted on the peer's mbarrier
-__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
-                                                uint32_t mbar_cluster) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
-      : "memory");
-}
-// K-major SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms of 512 bytes, atoms 1024 bytes apart
-__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (4ull << 61);
-}
-// byte offset of the hi element (row, kk) inside a K-block (kk in [0,32)); lo is 512 bytes further
-__device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
-  const int r = row & 7;
-  return (uint32_t)((row >> 3) * 1024 + r * 64 + ((((kk >> 3) ^ (r >> 1)) & 3) << 4) + (kk & 7) * 2);
-}
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
 // sigma(x) and tanh(x) from ex2.approx / rcp.approx: ~3e-7 absolute error, far inside the bf16x3
 // error of the recurrent product, and 4-5x shorter than expf/tanhf on the step's critical path
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -17,7 +17,7 @@ FFT_STRIDE = 64
 # 0 = exact fp32 SIMT kernels, 1 = tcgen05 (bf16x3 split operands, fp32 accumulate)
 DEFAULT_BACKEND = int(os.environ.get('DANET_BACKEND', '1'))
 
-TC_LSTM_MAX_H = 320
+TC_LSTM_MAX_H = 384
 
 # launch counter: bench.py reports how many of OUR kernels ran inside the timed region
 launches = 0
@@ -421,7 +421,7 @@ def head_bwd(embed, attractors, mix, src, perm_idx, kind, est_mode, src_pwr=None
     return {'d_embed': d_embed, 'd_attractors': d_attr, 'd_anchors': d_anchors}
 
 
-def lstm_seq_bwd(d_out, gates, cell, w_list, in_dim, T, B, H):
+def lstm_seq_bwd(d_out, gates, cell, w_list, in_dim, T, B, H, backend=None):
     """
     Backward through time [TF autodiff of main.py:125-131]: d_out [B,T,n_dir*H], gates [n_dir,T,B,4H]
     (post-activation, from lstm_seq(keep_gates=True)) are overwritten IN PLACE with the pre-activation
@@ -440,8 +440,9 @@ def lstm_seq_bwd(d_out, gates, cell, w_list, in_dim, T, B, H):
         ptrs[d] = w.data_ptr() + in_dim * 4 * H * 4
     lib = _lib.load()
     ws = _ws(lib.danet_lstm_seq_bwd_workspace_bytes(n_dir, B, H), gates.device)
+    be = (DEFAULT_BACKEND if H <= TC_LSTM_MAX_H else 0) if backend is None else backend
     _lib.check(lib.danet_lstm_seq_bwd(_p(d_out), _p(gates), _p(cell), ptrs, 4 * H, n_dir, T, B, H, _p(ws), ws.numel(),
-                                      _stream()), 'lstm_seq_bwd')
+                                      be, _stream()), 'lstm_seq_bwd')
     _count(2)
     return gates
 

@@ -117,11 +117,12 @@ int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long 
 /* backward through time (TF autodiff of the tf.scan at main.py:125-131): walks the sequence in
  * reverse, dh = d_out_t + da_{t+1} Wh^T, and overwrites `gates` ([g|i|f|o] from the forward) with
  * the pre-activation gradients da in place.  dWx / dWh / dX are danet_gemm calls on da;
- * the bias gradient is danet_colsum.  Exact fp32 cooperative kernel. */
+ * the bias gradient is danet_colsum.  backend 0 = exact fp32 cooperative kernel, 1 = tcgen05
+ * cluster kernel (Wh^T slices resident in TMEM, partial products reduce-scattered over DSMEM). */
 size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H);
 int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
                        const float* const* host_Wh, long long ldw, int n_dir, int T, int B, int H,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       void* workspace, size_t workspace_bytes, int backend, void* stream);
 /* out[n] (+)= sum over rows of x[rows, n] (row stride ld): bias gradients. workspace: 64*n floats */
 size_t danet_colsum_workspace_bytes(int n);
 int danet_colsum(const float* x, long long ld, long long rows, int n, float* out, int accumulate,

@@ -453,10 +453,10 @@ def test_head_backward(K, kind, est, B, C, T, E):
 
 
 # ---------------------------------------------------------------- training step (row a16)
-def test_lstm_layer_backward(K):
-    """BPTT kernel + dW/dX products of one BiLSTM layer against torch autograd on the oracle"""
+@pytest.mark.parametrize('B,T,I,H', [(3, 9, 40, 64), (9, 14, 129, 300), (17, 6, 600, 300)])
+def test_lstm_layer_backward(K, B, T, I, H):
+    """BPTT kernels (fp32 and tcgen05) + dW/dX products of one BiLSTM layer against torch autograd on the oracle"""
     rs = np.random.RandomState(11)
-    B, T, I, H = 3, 9, 40, 64
     r = .75 / np.sqrt(H)
     x = rs.standard_normal((B, T, I)).astype(np.float32)
     Ws = [rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32) for _ in range(2)]
@@ -476,7 +476,7 @@ def test_lstm_layer_backward(K):
         p = pre.clone()
         out, cell = K.lstm_seq(p, Wg, I, T, B, H, backend=backend, keep_cell=True, keep_gates=True)
         assert rel(out, y) < 1e-4
-        da = K.lstm_seq_bwd(cuda(dout), p, cell, Wg, I, T, B, H)
+        da = K.lstm_seq_bwd(cuda(dout), p, cell, Wg, I, T, B, H, backend=backend)
         dx = torch.zeros(B * T, I, device='cuda')
         for d in range(2):
             da_d = da[d].view(T * B, 4 * H)

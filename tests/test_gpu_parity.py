@@ -532,3 +532,62 @@ def test_model_gradients_golden(D, path):
         got = g.reshape(-1)[d['grad_idx.' + key]]
         ref = d['grad_val.' + key]
         assert np.abs(got - ref).max() <= TOL * max(np.abs(ref).max(), 1e-30) + 1e-6 * ref_l2, n
+
+
+# ---------------------------------------------------------------- BASELINE.json configs at full size (properties)
+def _set_hparams(D, **kw):
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(D.Hyperparameter().__dict__)
+    D.hparams.load(kw)
+    D.hparams.digest()
+    D.kernels.DEFAULT_BACKEND = 1
+
+
+def _shaped_noise(B, n, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    x = torch.randn(B, n, device='cuda', generator=g)
+    env = 0.5 - 0.5 * torch.cos(2 * np.pi * 4. * torch.arange(n, device='cuda') / 8000. + 1.3)
+    return x * env * 1000.
+
+
+@pytest.mark.parametrize('cfg', ['cfg2', 'cfg4', 'cfg5'])
+def test_full_size_configs(D, cfg):
+    """configs[1] (B=32, 4 s, E=20, anchor), configs[3] (B=16, 3 spk, 8 s, E=40, k-means 5 iter) and configs[4]
+    (B=1, 30 s stream) at full size: softmax masks sum to one, so the separated spectra / waveforms add up to the
+    mixture (linearity of the iSTFT), everything is finite, and the graphed path equals the eager one."""
+    K = D.kernels
+    if cfg == 'cfg2':
+        B, n, C, E, est = 32, 32000, 2, 20, 'anchor'
+    elif cfg == 'cfg4':
+        B, n, C, E, est = 16, 64000, 3, 40, 'kmeans'
+    else:
+        B, n, C, E, est = 1, 240000, 2, 20, 'anchor'
+    _set_hparams(D, ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD=est, INFER_ESTIMATOR_METHOD=est,
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=B, MAX_N_SIGNAL=C, EMBED_SIZE=E)
+    model = D.Model(cfg).build()
+    wav = _shaped_noise(B, n, 5)
+    T = K.num_frames(n)
+    assert T == {32000: 501, 64000: 1001, 240000: 3751}[n]
+    out = model.separate(wav)
+    assert out.shape == (B, C, 64 * T) and bool(torch.isfinite(out).all())
+    mix_back = K.istft(K.stft(wav))
+    err = (out.sum(1) - mix_back).abs().max() / mix_back.abs().max()
+    assert float(err) < 1e-4
+    # spectra level: sum_c mask_c * mix == mix
+    mix, logmag = K.stft(wav, want_logmag=True)
+    sep = model.infer(mix, logmag=logmag)
+    assert float((sep.sum(1) - mix).abs().max() / mix.abs().max()) < 1e-5
+    again = model.separate_graphed(wav)
+    assert float((again - out).abs().max()) == 0.
+
+
+def test_train_step_reduces_loss(D):
+    """cfg 2 training step (anchor + softmax, Adam 3e-4, clip 100) on a fixed batch: the loss goes down"""
+    K = D.kernels
+    _set_hparams(D, ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=8)
+    model = D.Model('train').build()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    src = K.stft(torch.randn(8, 2, 8000, device='cuda', generator=g) * 1000.)
+    losses = [float(model.train_step(src)['loss']) for _ in range(8)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

@@ -7,7 +7,7 @@ module of that name at the repository root; the directory name carries a hyphen)
 """
 from . import _lib, build, kernels, shard
 from .hparams import hparams, Hyperparameter
-from . import modules
+from . import modules, datasets, ozers
 from .modules import Encoder, Estimator, Separator, ModelModule
 from .model import Model
 

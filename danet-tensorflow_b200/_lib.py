@@ -24,6 +24,8 @@ PROTOTYPES = {
     'danet_mix_features_fwd': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_v]),
     'danet_center_workspace_bytes': (c_sz, [c_i]),
     'danet_center_fwd': (c_i, [c_f, c_i, c_ll, c_f, c_f, c_v]),
+    'danet_leaky_relu_bwd': (c_i, [c_f, c_f, c_f, c_ll, C.c_float, c_v]),
+    'danet_leaky_relu_fwd': (c_i, [c_f, c_f, c_ll, C.c_float, c_v]),
     'danet_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'danet_linear_fwd': (c_i, [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
     'danet_gemm_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
@@ -36,6 +38,7 @@ PROTOTYPES = {
     'danet_lstm_seq_bwd': (c_i, [c_f, c_f, c_f, C.POINTER(C.c_void_p), c_ll, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
     'danet_colsum_workspace_bytes': (c_sz, [c_i]),
     'danet_colsum': (c_i, [c_f, c_ll, c_ll, c_i, c_f, c_i, c_v, c_sz, c_v]),
+    'danet_clip_sgd': (c_i, [c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, c_v]),
     'danet_clip_adam': (c_i, [c_f, c_f, c_f, c_f, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, c_i, c_v]),
     'danet_attractor_workspace_bytes': (c_sz, [c_i, c_i, c_i]),

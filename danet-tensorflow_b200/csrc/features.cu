@@ -69,9 +69,49 @@ center_apply_kernel(const float* __restrict__ x, long long n_per, const float* _
     yb[i] = xb[i] - m;
 }
 
+__global__ void __launch_bounds__(256)
+leaky_relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float leak) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = x[i];
+    y[i] = leak == 0.f ? fmaxf(v, 0.f) : fmaxf(v * leak, v);     // app/ops.py:103-107
+  }
+}
+
+__global__ void __launch_bounds__(256)
+leaky_relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long n,
+                      float leak) {
+  // the activation is monotone, so the sign of the OUTPUT tells the branch
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    dx[i] = y[i] > 0.f ? dy[i] : dy[i] * leak;
+}
+
 }  // namespace danet
 
 using namespace danet;
+
+extern "C" int danet_leaky_relu_bwd(const float* y, const float* dy, float* dx, long long n, float leak, void* stream) {
+  DANET_REQUIRE(y && dy && dx, DANET_E_ARG, "leaky_relu_bwd: null pointer");
+  DANET_REQUIRE(n >= 0, DANET_E_SHAPE, "leaky_relu_bwd: n %lld", n);
+  if (n == 0) return DANET_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  leaky_relu_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(y, dy, dx, n, leak);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_leaky_relu_fwd(const float* x, float* y, long long n, float leak, void* stream) {
+  DANET_REQUIRE(x && y, DANET_E_ARG, "leaky_relu: null pointer");
+  DANET_REQUIRE(n >= 0, DANET_E_SHAPE, "leaky_relu: n %lld", n);
+  if (n == 0) return DANET_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  leaky_relu_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, y, n, leak);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
 
 extern "C" int danet_mix_features_fwd(const float* src_c64, int B, int C, int TF, float* mix_c64,
                                       float* src_pwr, float* mix_pwr, float* logmag, void* stream) {

@@ -42,9 +42,32 @@ clip_adam_kernel(float* __restrict__ param, const float* __restrict__ grad, floa
   }
 }
 
+__global__ void __launch_bounds__(256)
+clip_sgd_kernel(float* __restrict__ param, const float* __restrict__ grad, long long n, float grad_scale, float clip,
+                float lr) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float g = grad[i] * grad_scale;
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
+    param[i] -= lr * g;
+  }
+}
+
 }  // namespace danet
 
 using namespace danet;
+
+extern "C" int danet_clip_sgd(float* param, const float* grad, long long n, float grad_scale, float clip, float lr,
+                              void* stream) {
+  DANET_REQUIRE(param && grad, DANET_E_ARG, "clip_sgd: null pointer");
+  DANET_REQUIRE(n >= 0, DANET_E_SHAPE, "clip_sgd: n %lld", n);
+  if (n == 0) return DANET_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  clip_sgd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, n, grad_scale, clip, lr);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
 
 extern "C" size_t danet_colsum_workspace_bytes(int n) { return (size_t)(n > 0 ? n : 1) * kColParts * sizeof(float); }
 

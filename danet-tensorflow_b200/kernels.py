@@ -123,6 +123,23 @@ def center(x, out=None):
     return y
 
 
+def leaky_relu(x, leak=0., inplace=True):
+    """max(x*leak, x) [app/ops.py:93-107]"""
+    x = _req(x, 'x')
+    y = x if inplace else torch.empty_like(x)
+    _lib.check(_lib.load().danet_leaky_relu_fwd(_p(x), _p(y), x.numel(), float(leak), _stream()), 'leaky_relu')
+    _count()
+    return y
+
+
+def leaky_relu_bwd(y, dy, leak=0.):
+    """in place on dy: dy * (y > 0 ? 1 : leak)"""
+    y, dy = _req(y, 'y'), _req(dy, 'dy')
+    _lib.check(_lib.load().danet_leaky_relu_bwd(_p(y), _p(dy), _p(dy), y.numel(), float(leak), _stream()), 'leaky_relu_bwd')
+    _count()
+    return dy
+
+
 def linear(a, w, bias=None, time_major_T=0, backend=None, k_rows=None, row_offset=0, out=None):
     """
     a [M,K] @ w[row_offset : row_offset+K, :] (+ bias) -> [M,N]   [app/ops.py:72-89]
@@ -471,4 +488,11 @@ def clip_adam(param, grad, m, v, step, lr=3e-4, clip=100., beta1=.9, beta2=.999,
     _lib.check(_lib.load().danet_clip_adam(_p(param), _p(grad), _p(m), _p(v), param.numel(), grad_scale,
                                            clip if clip is not None else 0., lr, beta1, beta2, eps, int(step),
                                            _stream()), 'clip_adam')
+    _count()
+
+
+def clip_sgd(param, grad, lr, clip=100., grad_scale=1.):
+    """in place: clip_by_value then gradient descent [app/ozers.py:9-12]"""
+    _lib.check(_lib.load().danet_clip_sgd(_p(param), _p(grad), param.numel(), grad_scale,
+                                          clip if clip is not None else 0., lr, _stream()), 'clip_sgd')
     _count()

@@ -14,6 +14,7 @@ import torch
 from . import kernels as K
 from . import shard
 from . import modules as _modules   # noqa: F401  (registers the plugins, like app/__init__.py:1-5)
+from . import ozers as _ozers       # noqa: F401
 from .hparams import hparams
 
 
@@ -155,13 +156,11 @@ class Model(object):
         feats = K.mix_features(src)
         # ---- forward, recording what the backward needs
         enc = self.encoder
-        n_layers, hdim = enc._geometry()
         self._tape = []
         try:
             embed = enc(feats['logmag'])
         finally:
             tape, self._tape = self._tape, None
-        xc = self._last_centered                                      # input of the output projection
         embed_flat = embed.view(B, T * F, E)
         if est_name == 'anchor':
             anchors = self.estimator.anchors()
@@ -177,31 +176,7 @@ class Model(object):
                        src_pwr=feats['src_pwr'], mix_pwr=feats['mix_pwr'], anchors=anchors, choice=choice, den=den)
         if est_name == 'anchor':
             grads[self.estimator.name + '/anchors'].copy_(g['d_anchors'])
-        dV = g['d_embed'].view(B * T, F * E)
-        Wout = self.params[enc.name + '/output/W']
-        K.gemm(xc.view(B * T, -1), dV, trans_a=True, out=grads[enc.name + '/output/W'])     # dW = X^T dY
-        dx = K.gemm(dV, Wout, trans_b=True)                                                 # dX = dY W^T
-        dx = K.center(dx.view(B, T, -1))                      # gradient of x - mean(x) is the same centring
-        for l in range(n_layers - 1, -1, -1):
-            rec = tape[l]
-            H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
-            names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if enc.BIDIR else [rec['name']]
-            Ws = [self.params[n + '/LSTM/linear/W'] for n in names]
-            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)              # [n_dir,T,B,4H]
-            x2 = x.reshape(B * T, I)
-            out2 = rec['out'].view(B * T, -1)
-            dx_prev = torch.empty((B * T, I), dtype=torch.float32, device=src.device) if l > 0 else None
-            for d, n in enumerate(names):
-                da_d = da[d].view(T * B, 4 * H)
-                dW = grads[n + '/LSTM/linear/W']
-                K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                      # dWx = sum X[b,t]^T da[t,b]
-                K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,          # dWh = sum h[b,t-+1]^T da[t,b]
-                       shift_a=-1 if d == 0 else 1, out=dW[I:])
-                K.colsum(da_d, out=grads[n + '/LSTM/linear/B'])
-                if l > 0:
-                    K.gemm(da_d, Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
-            if l > 0:
-                dx = dx_prev.view(B, T, I)
+        enc.backward(g['d_embed'].view(B * T, F * E), tape)
         return dict(loss=pit['loss'][0], snr=pit['snr'].mean(), perm_idx=pit['perm_idx'])
 
     def all_reduce_grads(self):
@@ -214,21 +189,28 @@ class Model(object):
         return 1.
 
     def apply_gradients(self, grad_scale=1.):
-        """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then Adam, one fused launch over all variables"""
+        """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then the registered optimiser (app/ozers.py), one fused
+        launch over the flat parameter buffer"""
         self.step_count += 1
         f = self._flat
-        K.clip_adam(f['param'], f['grad'], f['m'], f['v'], self.step_count, lr=hparams.LR,
-                    clip=hparams.GRAD_CLIP_THRES)
+        opt = hparams.get_optimizer()(hparams.LR)
+        if opt['kind'] == 'adam':
+            K.clip_adam(f['param'], f['grad'], f['m'], f['v'], self.step_count, lr=opt['lr'], clip=hparams.GRAD_CLIP_THRES,
+                        beta1=opt['beta1'], beta2=opt['beta2'], eps=opt['eps'], grad_scale=grad_scale)
+        else:
+            K.clip_sgd(f['param'], f['grad'], opt['lr'], clip=hparams.GRAD_CLIP_THRES, grad_scale=grad_scale)
 
     def train_step(self, src):
-        """train fetches (main.py:369-375): forward, backward, gradient all-reduce, clip + Adam"""
+        """train fetches (main.py:369-375): forward, backward, gradient all-reduce, clip + optimiser"""
         out = self.train_forward_backward(src)
-        scale = self.all_reduce_grads()
-        self.step_count += 1
-        f = self._flat
-        K.clip_adam(f['param'], f['grad'], f['m'], f['v'], self.step_count, lr=hparams.LR,
-                    clip=hparams.GRAD_CLIP_THRES, grad_scale=scale)
+        self.apply_gradients(self.all_reduce_grads())
         return out
+
+    def set_learn_rate(self, lr):
+        hparams.LR = float(lr)                                   # main.py:541-548
+
+    def get_learn_rate(self):
+        return hparams.LR
 
     # ---------------------------------------------------------------- assembly
     def build(self):

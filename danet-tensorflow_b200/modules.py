@@ -3,7 +3,7 @@ Encoder / Estimator / Separator plugins -- the reference's app/modules.py surfac
 (`cls(model, name)`, called like functions, registered with `@hparams.register_*`) on
 CUDA tensors, every computation a call into libdanet_sm100.so (`kernels.py`).
 
-Registered names: encoders `lstm-orig`, `bilstm-orig`; estimators `truth`,
+Registered names: encoders `toy`, `lstm-orig`, `bilstm-orig`; estimators `truth`,
 `truth-threshold`, `truth-weighted`, `anchor`, `kmeans` (new); separators
 `dot-sigmoid-orig`, `dot-softmax-orig`.
 """
@@ -73,6 +73,43 @@ def _lyr_bilstm(name, model, s_input, hdim, w_init, b_init, s_dropout_keep=1.):
     return model.lyr_bilstm(name, s_input, hdim, w_init=w_init, b_init=b_init)
 
 
+def _glorot_uniform(rs, shape):
+    lim = sqrt(6. / (shape[0] + shape[1]))          # TF1's default initialiser of tf.get_variable
+    return rs.uniform(-lim, lim, size=shape)
+
+
+def _zeros(rs, shape):
+    return np.zeros(shape)
+
+
+@hparams.register_encoder('toy')
+class ToyEncoder(Encoder):
+    """app/modules.py:96-116: 129 -> 2*FFT_SIZE -> F*E MLP with a leaky ReLU (the reference's default)"""
+    def __call__(self, s_signals, s_dropout_keep=1.):
+        model = self.model
+        B, T, F = s_signals.shape
+        E, hid = hparams.EMBED_SIZE, hparams.FFT_SIZE * 2
+        W0 = model.get_variable('%s/linear0/W' % self.name, [F, hid], _glorot_uniform)
+        B0 = model.get_variable('%s/linear0/B' % self.name, [hid], _zeros)
+        W1 = model.get_variable('%s/linear1/W' % self.name, [hid, F * E], _glorot_uniform)
+        B1 = model.get_variable('%s/linear1/B' % self.name, [F * E], _zeros)
+        x2 = s_signals.reshape(B * T, F)
+        mid = K.leaky_relu(K.linear(x2, W0, B0), hparams.RELU_LEAKAGE)
+        if model._tape is not None:
+            model._tape.append(dict(x=x2, mid=mid))
+        return K.linear(mid, W1, B1).view(B, T, F, E)
+
+    def backward(self, d_embed2, tape):
+        """d_embed2 [B*T, F*E] -> fills model.grads (what tf.gradients derives for the two dense layers)"""
+        g, P, n = self.model.grads, self.model.params, self.name
+        rec = tape[0]
+        K.gemm(rec['mid'], d_embed2, trans_a=True, out=g[n + '/linear1/W'])
+        K.colsum(d_embed2, out=g[n + '/linear1/B'])
+        dmid = K.leaky_relu_bwd(rec['mid'], K.gemm(d_embed2, P[n + '/linear1/W'], trans_b=True), hparams.RELU_LEAKAGE)
+        K.gemm(rec['x'], dmid, trans_a=True, out=g[n + '/linear0/W'])
+        K.colsum(dmid, out=g[n + '/linear0/B'])
+
+
 class _RecurrentEncoder(Encoder):
     N_LAYERS = 4
     HDIM = 300
@@ -99,7 +136,8 @@ class _RecurrentEncoder(Encoder):
             else:
                 x = model.lyr_lstm('%s/lstm%d' % (self.name, l), x, hdim, w_init=w_init, b_init=b_init)
         x = K.center(x)                                            # modules.py:244-245 / :181-182
-        model._last_centered = x
+        if model._tape is not None:
+            model._tape.append(dict(centered=x))
         odim = x.shape[-1]
         E = hparams.EMBED_SIZE
         W = model.get_variable('%s/output/W' % self.name, [odim, F * E], _uniform(-1.85, 1.85))
@@ -108,6 +146,38 @@ class _RecurrentEncoder(Encoder):
         if hparams.DEBUG:
             self.debug_fetches['embed'] = s_out
         return s_out
+
+
+    def backward(self, d_embed2, tape):
+        """d_embed2 [B*T, F*E] -> fills model.grads: output projection, centring, then per layer the BPTT kernel
+        and the dWx / dWh / db / dX products on its in-place gate gradients"""
+        model = self.model
+        g, P = model.grads, model.params
+        xc = tape[-1]['centered']
+        B, T, odim = xc.shape
+        K.gemm(xc.view(B * T, odim), d_embed2, trans_a=True, out=g[self.name + '/output/W'])     # dW = X^T dY
+        dx = K.gemm(d_embed2, P[self.name + '/output/W'], trans_b=True)                          # dX = dY W^T
+        dx = K.center(dx.view(B, T, odim))             # the gradient of x - mean(x) is the same centring
+        for l in range(len(tape) - 2, -1, -1):
+            rec = tape[l]
+            H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
+            names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if self.BIDIR else [rec['name']]
+            Ws = [P[n + '/LSTM/linear/W'] for n in names]
+            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)                   # [n_dir,T,B,4H]
+            x2 = x.reshape(B * T, I)
+            out2 = rec['out'].view(B * T, -1)
+            dx_prev = K.torch.empty((B * T, I), dtype=K.torch.float32, device=x.device) if l > 0 else None
+            for d, n in enumerate(names):
+                da_d = da[d].view(T * B, 4 * H)
+                dW = g[n + '/LSTM/linear/W']
+                K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                           # sum X[b,t]^T da[t,b]
+                K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,               # sum h[b,t-+1]^T da[t,b]
+                       shift_a=-1 if d == 0 else 1, out=dW[I:])
+                K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
+                if l > 0:
+                    K.gemm(da_d, Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
+            if l > 0:
+                dx = dx_prev.view(B, T, I)
 
 
 @hparams.register_encoder('lstm-orig')

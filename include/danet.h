@@ -68,6 +68,11 @@ size_t danet_center_workspace_bytes(int B);
 int danet_center_fwd(const float* x, int B, long long n_per, float* y,
                      float* workspace, void* stream);
 
+/* leaky ReLU of the `toy` encoder: y = max(x*leak, x) (app/ops.py:93-107); y may alias x */
+int danet_leaky_relu_fwd(const float* x, float* y, long long n, float leak, void* stream);
+/* dx = dy * (y > 0 ? 1 : leak), from the activation's OUTPUT y; dx may alias dy */
+int danet_leaky_relu_bwd(const float* y, const float* dy, float* dx, long long n, float leak, void* stream);
+
 /* ---- dense layers (input projections of the LSTM, output projection) ------
  * replaces app/ops.py:37-90 (lyr_linear, last-axis branch :72-89).
  * C[M,N] = A[M,K] (row stride lda) * W[K,N] (row stride ldw) (+ bias[N]).
@@ -132,6 +137,9 @@ int danet_colsum(const float* x, long long ld, long long rows, int n, float* out
  * the gradient first (1/world_size after an all-reduce sum).  clip <= 0 disables clipping. */
 int danet_clip_adam(float* param, const float* grad, float* m, float* v, long long n, float grad_scale,
                     float clip, float lr, float beta1, float beta2, float eps, int step, void* stream);
+/* clip_by_value then tf.train.GradientDescentOptimizer (app/ozers.py:9-12) */
+int danet_clip_sgd(float* param, const float* grad, long long n, float grad_scale, float clip, float lr,
+                   void* stream);
 
 /* ---- K3  attractor estimation ---------------------------------------------
  * truth family replaces app/modules.py:390-412 (mode 0: plain, denominator n+1),

@@ -250,7 +250,9 @@ lstm_bwd_tc_kernel(const LstmBwdTcParams p) {
             float v[NB];
             if (NB == 16) tmem_ld_32x16(tmem_acc + 32 * t + ((uint32_t)(32 * warp) << 16), *reinterpret_cast<float(*)[16]>(v));
             else tmem_ld_32x8(tmem_acc + 32 * t + ((uint32_t)(32 * warp) << 16), *reinterpret_cast<float(*)[8]>(v));
-            float4* o = reinterpret_cast<float4*>(stg + ((size_t)peer * 32 + lane) * NB);
+            // the slice for my own units goes straight into my receive table (no transport needed)
+            float* base = peer == rank ? sRecv + (size_t)(n & 1) * kBwMaxCta * 32 * NB : stg;
+            float4* o = reinterpret_cast<float4*>(base + ((size_t)peer * 32 + lane) * NB);
 #pragma unroll
             for (int j = 0; j < NB / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
@@ -269,11 +271,15 @@ lstm_bwd_tc_kernel(const LstmBwdTcParams p) {
     for (int n = 0; n + 1 < T; ++n) {
       asm volatile("bar.sync 1, %0;" ::"r"(kBwEpi + 32 * ncta) : "memory");
       if (elect_one_sync()) {
-        const uint32_t boff = (uint32_t)(n & 1) * kBwMaxCta * 32 * NB * 4;
-        const uint32_t bar = peer_bar + (uint32_t)(n & 1) * 8;
-        mbar_arrive_expect_tx_cluster(bar, kSlice);
-        dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (size_t)(n & 1) * kBwMaxCta * 32 * NB + (size_t)peer * 32 * NB),
-                        kSlice, bar);
+        if (peer == rank) {
+          mbar_arrive(p_full + (n & 1));                        // own slice: written in place by the epilogue
+        } else {
+          const uint32_t boff = (uint32_t)(n & 1) * kBwMaxCta * 32 * NB * 4;
+          const uint32_t bar = peer_bar + (uint32_t)(n & 1) * 8;
+          mbar_arrive_expect_tx_cluster(bar, kSlice);
+          dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (size_t)(n & 1) * kBwMaxCta * 32 * NB + (size_t)peer * 32 * NB),
+                          kSlice, bar);
+        }
       }
       __syncwarp();
     }

@@ -245,15 +245,23 @@ lstm_tc_kernel(const LstmTcParams p) {
         __nv_bfloat16 hi[UPT], lo[UPT];
 #pragma unroll
         for (int uu = 0; uu < UPT; ++uu) split_bf16(h[uu], hi[uu], lo[uu]);
+        // staged once for the peers, and written straight into this CTA's own B operand (a bulk copy whose
+        // destination is the issuing CTA is not a remote access; the own slice needs no transport at all)
         uint8_t* st = sStage + (s & 1) * kHBlock;
+        uint8_t* own = sH + ((size_t)(s & 1) * ncta + rank) * kHBlock;
         if (UPT == 4) {
-          *reinterpret_cast<uint2*>(st + stage_off) =
-              make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[UPT - 2], hi[UPT - 1]));
-          *reinterpret_cast<uint2*>(st + 512 + stage_off) =
-              make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[UPT - 2], lo[UPT - 1]));
+          const uint2 vh = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[UPT - 2], hi[UPT - 1]));
+          const uint2 vl = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[UPT - 2], lo[UPT - 1]));
+          *reinterpret_cast<uint2*>(st + stage_off) = vh;
+          *reinterpret_cast<uint2*>(st + 512 + stage_off) = vl;
+          *reinterpret_cast<uint2*>(own + stage_off) = vh;
+          *reinterpret_cast<uint2*>(own + 512 + stage_off) = vl;
         } else {
-          *reinterpret_cast<uint32_t*>(st + stage_off) = pack_bf16(hi[0], hi[1]);
-          *reinterpret_cast<uint32_t*>(st + 512 + stage_off) = pack_bf16(lo[0], lo[1]);
+          const uint32_t vh = pack_bf16(hi[0], hi[1]), vl = pack_bf16(lo[0], lo[1]);
+          *reinterpret_cast<uint32_t*>(st + stage_off) = vh;
+          *reinterpret_cast<uint32_t*>(st + 512 + stage_off) = vl;
+          *reinterpret_cast<uint32_t*>(own + stage_off) = vh;
+          *reinterpret_cast<uint32_t*>(own + 512 + stage_off) = vl;
         }
         fence_proxy_async_smem();
         // hand the staged slice to the sender warps (producer side of named barrier 1: no wait)
@@ -289,10 +297,14 @@ lstm_tc_kernel(const LstmTcParams p) {
     for (int s = 0; s + 1 < T; ++s) {
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads + 32 * ncta) : "memory");
       if (elect_one_sync()) {
-        const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kHBlock;
-        const uint32_t bar = peer_bar + (uint32_t)(s & 1) * 8;
-        mbar_arrive_expect_tx_cluster(bar, kSendBytes);     // one arrival + the byte count, posted by the sender
-        dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (s & 1) * kHBlock), kSendBytes, bar);
+        if (peer == rank) {
+          mbar_arrive(h_full + (s & 1));                      // own slice: already in place, just count it
+        } else {
+          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kHBlock;
+          const uint32_t bar = peer_bar + (uint32_t)(s & 1) * 8;
+          mbar_arrive_expect_tx_cluster(bar, kSendBytes);     // one arrival + the byte count, posted by the sender
+          dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (s & 1) * kHBlock), kSendBytes, bar);
+        }
         DANET_PROF(9);
       }
       __syncwarp();

@@ -85,6 +85,8 @@ struct GemmParams {
   long long ldc;
   int M, N, n_kblocks, T, nb;   // T > 0: logical row b*T+t is stored at row t*nb+b
   int accumulate;               // C += instead of C =
+  int kb_per_split;             // K blocks per blockIdx.z (split-K: partial sums are added atomically)
+  int atomic;                   // 1 when gridDim.z > 1
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -99,7 +101,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
-  const int nkb = p.n_kblocks;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, p.n_kblocks - kb0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -127,10 +130,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(empty_bar + s, ph ^ 1);
         uint8_t* st = smem + s * kStageBytes;
         mbar_arrive_expect_tx(full_bar + s, kStageBytes);
-        tma_load_2d(st, &map_a, full_bar + s, kb * kTK, m0);                          // A hi
-        tma_load_2d(st + kTileBytes, &map_a, full_bar + s, kb * kTK, p.M + m0);       // A lo
-        tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + s, kb * kTK, n0);         // W^T hi
-        tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + s, kb * kTK, p.N + n0);   // W^T lo
+        const int kc = (kb0 + kb) * kTK;
+        tma_load_2d(st, &map_a, full_bar + s, kc, m0);                          // A hi
+        tma_load_2d(st + kTileBytes, &map_a, full_bar + s, kc, p.M + m0);       // A lo
+        tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + s, kc, n0);         // W^T hi
+        tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + s, kc, p.N + n0);   // W^T lo
       }
     }
   } else if (warp == 1) {
@@ -170,7 +174,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (n0 + c0 >= p.N) break;                       // warp-uniform
       float v[32];
       tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v);
-      if (row_ok) {
+      if (row_ok && p.atomic) {
+        // split-K: every K slice adds its partial tile (C was zeroed, or holds the value to accumulate onto)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) atomicAdd(crow + n, v[j] + ((p.bias && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f));
+        }
+      } else if (row_ok) {
         if (vec && n0 + c0 + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -290,6 +301,29 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& B, const float* bias, float
   DANET_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
   dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
   DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "gemm: M %d too large", M);
+  // split-K when the output has too few tiles to fill the SMs and the reduction is long (dW = X^T dY:
+  // 30-50 tiles, K = B*T): slices of >= 8 K blocks, partial tiles added with red.global.add.f32
+  {
+    const int tiles = (int)(grid.x * grid.y), sms = num_sms();
+    int splits = 1;
+    if (tiles * 2 <= sms && p.n_kblocks >= 16) {
+      splits = sms / tiles;
+      const int max_splits = p.n_kblocks / 8;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+    p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
+    splits = (p.n_kblocks + p.kb_per_split - 1) / p.kb_per_split;
+    grid.z = splits;
+    p.atomic = splits > 1;
+    if (p.atomic && !accumulate) {
+      if (ldc == N) {
+        DANET_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), stream));
+      } else {
+        DANET_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
+      }
+    }
+  }
   gemm_bf16x3_kernel<<<grid, 256, kGemmSmem, stream>>>(map_a, map_b, p);
   DANET_LAUNCH_CHECK();
   return DANET_OK;

@@ -21,7 +21,7 @@ constexpr int kMaxAnchor = 8;
 constexpr int kParts = 32;        // blocks per utterance
 constexpr int kMaxAccPerThread = 4;
 
-enum { MODE_TRUTH = 0, MODE_ANCHOR = 1, MODE_KMEANS = 2 };
+enum { MODE_TRUTH = 0, MODE_ANCHOR = 1, MODE_KMEANS = 2, MODE_ANCHOR2 = 3 };
 
 struct AttParams {
   const float* embed;     // [B][TF][E]
@@ -93,6 +93,33 @@ __device__ __forceinline__ void row_weights(const AttParams& p, int b, long long
       for (int c = 0; c < kAttMaxC; ++c)
         if (c < C) w[s * C + c] = l[c] * inv;
     }
+  } else if (MODE == MODE_ANCHOR2) {
+    // two sources: softmax over a pair (a,b) is S_a = 1 / (1 + exp(l_b - l_a)), S_b = 1 - S_a.  Only S_a is
+    // accumulated; row P carries the constant weight 1, and the finalize kernel recovers the second member of
+    // every pair as (sum V - sum S_a V) / (N - sum S_a): half the eq.7 products.  Pairs in
+    // itertools.combinations order, indices compile-time after unrolling (no register-select chains).
+    float logit[kMaxAnchor];
+#pragma unroll
+    for (int a = 0; a < kMaxAnchor; ++a) logit[a] = 0.f;
+    for (int e = 0; e < E; e += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(v + e);
+#pragma unroll
+      for (int a = 0; a < kMaxAnchor; ++a)
+        if (a < p.n_anchor) {
+          const float4 an = *reinterpret_cast<const float4*>(sAux + a * E + e);
+          logit[a] = fmaf(x.x, an.x, logit[a]);
+          logit[a] = fmaf(x.y, an.y, logit[a]);
+          logit[a] = fmaf(x.z, an.z, logit[a]);
+          logit[a] = fmaf(x.w, an.w, logit[a]);
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int a = 0; a < kMaxAnchor; ++a)
+#pragma unroll
+      for (int bq = a + 1; bq < kMaxAnchor; ++bq)
+        if (bq < p.n_anchor) w[s++] = __fdividef(1.f, 1.f + __expf(logit[bq] - logit[a]));
+    w[s] = 1.f;
   } else {   // k-means: nearest centroid, first minimum on ties
     int k = 0;
     float best = INFINITY;
@@ -120,12 +147,13 @@ attractor_partial_rt_kernel(const AttParams p) {
   constexpr int E = 4 * NQ;
   const int C = p.C, R = p.R, ldv = p.ldv;
   float* sV = smem;                                  // [kTileRT][ldv]
-  float* sW = sV + kTileRT * ldv;                    // [kTileRT][R]
-  float* sAux = sW + kTileRT * R;                    // anchors / centroids (16-byte aligned: R*256 floats)
+  const int ldw = R | 1;                             // odd row stride: the per-bin weight stores are conflict-free
+  float* sW = sV + kTileRT * ldv;                    // [kTileRT][ldw]
+  float* sAux = sW + kTileRT * ldw;                  // anchors / centroids (16-byte aligned: ldw*256 floats)
   const int tid = threadIdx.x, b = blockIdx.y, part = blockIdx.x;
   const long long TF = p.TF;
   const float* Vb = p.embed + (size_t)b * TF * E;
-  const int n_aux = MODE == MODE_ANCHOR ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
+  const int n_aux = (MODE == MODE_ANCHOR || MODE == MODE_ANCHOR2) ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
   for (int i = tid; i < n_aux; i += 256)
     sAux[i] = MODE == MODE_KMEANS ? p.aux[(size_t)b * C * E + i] : p.aux[i];
 
@@ -153,11 +181,11 @@ attractor_partial_rt_kernel(const AttParams p) {
       }
     }
     __syncthreads();
-    row_weights<MODE>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * R);
+    row_weights<MODE>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * ldw);
     __syncthreads();
     if (active) {
       for (int tfl = g; tfl < n_here; tfl += G) {
-        const float wv = sW[tfl * R + r];
+        const float wv = sW[tfl * ldw + r];
         const float* vr = sV + tfl * ldv;
         den += wv;
 #pragma unroll
@@ -202,7 +230,7 @@ attractor_partial_kernel(const AttParams p) {
   const long long TF = p.TF;
   const float* Vb = p.embed + (size_t)b * TF * E;
 
-  const int n_aux = MODE == MODE_ANCHOR ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
+  const int n_aux = (MODE == MODE_ANCHOR || MODE == MODE_ANCHOR2) ? p.n_anchor * E : (MODE == MODE_KMEANS ? C * E : 0);
   for (int i = tid; i < n_aux; i += 256)
     sAux[i] = MODE == MODE_KMEANS ? p.aux[(size_t)b * C * E + i] : p.aux[i];
   for (int i = tid; i < kTile; i += 256) {   // constant "ones" quad feeding the denominators
@@ -280,16 +308,32 @@ __global__ void __launch_bounds__(256)
 attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, int nQ, int n_sub,
                           float denom_add, float* __restrict__ attractors,
                           float* __restrict__ attractor_sets, float* __restrict__ sims,
-                          int* __restrict__ choice, float* __restrict__ den_out) {
+                          int* __restrict__ choice, float* __restrict__ den_out, int halved) {
   __shared__ float s_sum[kAttMaxRows * (kAttMaxE + 4)];
   __shared__ float s_sim[32];
   __shared__ int s_choice;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int ld = nQ * 4, n = R * ld;
-  for (int i = tid; i < n; i += 256) {
-    float s = 0.f;
-    for (int pt = 0; pt < kParts; ++pt) s += part[((size_t)b * kParts + pt) * n + i];
-    s_sum[i] = s;
+  if (halved) {
+    // partial rows: n_sub first-member sums, then the all-ones row; expand to the [n_sub][2] rows of eq.7
+    const int np = (n_sub + 1) * ld;
+    for (int i = tid; i < n_sub * ld; i += 256) {
+      const int s = i / ld, e = i % ld;
+      float first = 0.f, total = 0.f;
+      for (int pt = 0; pt < kParts; ++pt) {
+        const float* pp = part + ((size_t)b * kParts + pt) * np;
+        first += pp[s * ld + e];
+        total += pp[n_sub * ld + e];
+      }
+      s_sum[(2 * s) * ld + e] = first;
+      s_sum[(2 * s + 1) * ld + e] = total - first;
+    }
+  } else {
+    for (int i = tid; i < n; i += 256) {
+      float s = 0.f;
+      for (int pt = 0; pt < kParts; ++pt) s += part[((size_t)b * kParts + pt) * n + i];
+      s_sum[i] = s;
+    }
   }
   __syncthreads();
   if (den_out)   // raw weight sums per row, kept for the backward pass
@@ -358,7 +402,7 @@ static size_t att_smem_bytes(int E, int R, int n_aux) {
 
 template <int MODE, int NQ>
 static int launch_partial_rt(AttParams& p, int B, int n_aux, cudaStream_t st) {
-  size_t tile = (size_t)kTileRT * p.ldv + (size_t)kTileRT * p.R + n_aux;
+  size_t tile = (size_t)kTileRT * p.ldv + (size_t)kTileRT * (p.R | 1) + n_aux;
   size_t red = (size_t)256 * (4 * NQ + 4);
   const size_t smem = (tile > red ? tile : red) * sizeof(float);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "attractor: %zu B of shared memory needed", smem);
@@ -432,7 +476,7 @@ extern "C" int danet_attractor_truth_fwd(const float* embed, const float* src_pw
   rc = launch_partial<MODE_TRUTH>(p, B, 0, as_stream(stream));
   if (rc) return rc;
   attractor_finalize_kernel<MODE_TRUTH><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr, den);
+      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr, den, 0);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
@@ -465,10 +509,17 @@ extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* ancho
       for (int j = i + 1; j < C; ++j) idx[j] = idx[j - 1] + 1;
     }
   }
-  rc = launch_partial<MODE_ANCHOR>(p, B, n_anchor * E, as_stream(stream));
+  const bool halved = C == 2 && (E == 4 || E == 12 || E == 20 || E == 40);   // fast path instantiations
+  if (halved) {
+    p.R = P + 1;
+    rc = launch_partial<MODE_ANCHOR2>(p, B, n_anchor * E, as_stream(stream));
+    p.R = P * C;
+  } else {
+    rc = launch_partial<MODE_ANCHOR>(p, B, n_anchor * E, as_stream(stream));
+  }
   if (rc) return rc;
   attractor_finalize_kernel<MODE_ANCHOR><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice, den);
+      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice, den, halved ? 1 : 0);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
@@ -488,7 +539,7 @@ extern "C" int danet_attractor_kmeans_fwd(const float* embed, float* centroids, 
     rc = launch_partial<MODE_KMEANS>(p, B, C * E, as_stream(stream));
     if (rc) return rc;
     attractor_finalize_kernel<MODE_KMEANS><<<B, 256, 0, as_stream(stream)>>>(
-        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr, nullptr);
+        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr, nullptr, 0);
     DANET_LAUNCH_CHECK();
   }
   return DANET_OK;

@@ -308,21 +308,36 @@ class Model(object):
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
     PIPELINE_MAX_GROUPS = 4
 
-    def separate(self, wav, groups=None):
-        """demo path (main.py:660-695): waveforms [B,N] f32 on the device -> [B,C,64*T] f32.
+    def separate(self, wav, groups=None, out=None):
+        """demo path (main.py:660-695): waveforms [B,N] f32 -> [B,C,64*T] f32.
         STFT (app/utils.py:117-122), infer graph, iSTFT per source (app/utils.py:53-75).
 
         Utterances are independent, and the recurrence is latency-bound on a fraction of the SMs, so
-        the batch is cut into groups that run the encoder / estimator / separator on their own CUDA
-        streams: one group's dense layers fill the SMs another group's recurrence leaves idle."""
-        B = wav.shape[0]
+        the batch is cut into groups that run front end / encoder / estimator / separator / back end on
+        their own CUDA streams: one group's dense layers fill the SMs another group's recurrence leaves
+        idle.  `wav` and `out` may be PINNED HOST tensors: each group then copies its own slice in and
+        out on its stream, so the PCIe transfers of one group overlap the compute of the others."""
+        B, n = wav.shape
         if groups is None:
             groups = max(1, min(self.PIPELINE_MAX_GROUPS, B // self.PIPELINE_GROUP))
-        mix, logmag = K.stft(wav, want_logmag=True)
+        Cn, T = hparams.MAX_N_SIGNAL, K.num_frames(n)
+        if out is None:
+            out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=self.device)
+
+        def run(lo, hi):
+            w = wav[lo:hi]
+            if not w.is_cuda:
+                w = w.to(self.device, non_blocking=True)
+            mix, logmag = K.stft(w, want_logmag=True)
+            sep = self.infer(mix, logmag=logmag)
+            if out.is_cuda:
+                K.istft(sep, out=out[lo:hi])
+            else:
+                out[lo:hi].copy_(K.istft(sep), non_blocking=True)
+
         if groups <= 1:
-            return K.istft(self.infer(mix, logmag=logmag))
-        Cn, T = hparams.MAX_N_SIGNAL, mix.shape[1]
-        out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=wav.device)
+            run(0, B)
+            return out
         main = torch.cuda.current_stream()
         fork = main.record_event()
         streams = self._side_streams(groups)
@@ -336,36 +351,37 @@ class Model(object):
                 st.wait_event(prev)
             with torch.cuda.stream(st):
                 self._stagger_pending, self._stagger_event = True, None
-                K.istft(self.infer(mix[lo:hi], logmag=logmag[lo:hi]), out=out[lo:hi])
+                run(lo, hi)
                 prev = self._stagger_event
                 self._stagger_pending = False
         for st in streams:
             main.wait_stream(st)
         return out
 
-    def separate_graphed(self, wav, groups=None):
-        """`separate` replayed from a CUDA graph captured once per input shape: ~100 kernel launches
-        and their host-side argument checks collapse into one graph launch.  Returns a static output
-        buffer that the next call overwrites."""
-        key = (tuple(wav.shape), groups)
+    def separate_graphed(self, wav, groups=None, out=None):
+        """`separate` replayed from a CUDA graph captured once per (buffers, shape): ~400 kernel launches
+        and their host-side argument checks collapse into one graph launch.  Device input: copied into a
+        static buffer, the returned static output is overwritten by the next call.  Pinned host `wav` / `out`:
+        the graph reads and writes those very buffers (their addresses are part of the key)."""
+        host_io = not wav.is_cuda
+        key = (tuple(wav.shape), groups, wav.data_ptr() if host_io else None, out.data_ptr() if out is not None else None)
         entry = self._graphs.get(key)
         if entry is None:
-            static_in = torch.empty_like(wav)
-            static_in.copy_(wav)
+            static_in = wav if host_io else torch.empty_like(wav).copy_(wav)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):                     # warm up: variables, function attributes, allocator
-                    self.separate(static_in, groups)
+                    self.separate(static_in, groups, out)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self.separate(static_in, groups)
+                static_out = self.separate(static_in, groups, out)
             entry = (graph, static_in, static_out)
             self._graphs[key] = entry
         graph, static_in, static_out = entry
-        if wav.data_ptr() != static_in.data_ptr():
+        if not host_io and wav.data_ptr() != static_in.data_ptr():
             static_in.copy_(wav, non_blocking=True)
         graph.replay()
         return static_out
@@ -377,10 +393,12 @@ class Model(object):
         return pool[:n]
 
     def separate_host(self, wav_host, out_host=None, graphed=True):
-        """The call a user makes: pinned host waveforms in, host waveforms out."""
-        wav = wav_host.to(self.device, non_blocking=True)
-        y = self.separate_graphed(wav) if graphed else self.separate(wav)
+        """The call a user makes: pinned host waveforms in, (pinned) host waveforms out; returns after
+        the results are in `out_host` only once the caller synchronises the current stream."""
         if out_host is None:
-            return y.cpu()
-        out_host.copy_(y, non_blocking=True)
-        return out_host
+            n = wav_host.shape[1]
+            out_host = torch.empty((wav_host.shape[0], hparams.MAX_N_SIGNAL, K.FFT_STRIDE * K.num_frames(n)),
+                                   dtype=torch.float32).pin_memory()
+        if graphed and wav_host.is_pinned() and out_host.is_pinned():
+            return self.separate_graphed(wav_host, out=out_host)
+        return self.separate(wav_host, out=out_host)

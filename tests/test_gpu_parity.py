@@ -592,3 +592,18 @@ def test_train_step_reduces_loss(D):
     src = K.stft(torch.randn(8, 2, 8000, device='cuda', generator=g) * 1000.)
     losses = [float(model.train_step(src)['loss']) for _ in range(8)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_separate_host_pinned_io(D):
+    """the user-facing call: pinned host buffers in and out, per-group transfers inside the CUDA graph"""
+    _set_hparams(D, ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=16)
+    model = D.Model('host').build()
+    wav = (_shaped_noise(16, 8000, 9)).cpu().pin_memory()
+    out = torch.empty((16, 2, 64 * D.kernels.num_frames(8000)), dtype=torch.float32).pin_memory()
+    ref = model.separate(wav.cuda(), groups=1).cpu()
+    for _ in range(3):                                   # capture, then replays
+        out.zero_()
+        model.separate_host(wav, out)
+        torch.cuda.synchronize()
+        assert float((out - ref).abs().max()) == 0.

@@ -39,3 +39,18 @@ extern "C" int danet_check_device(void) {
   DANET_REQUIRE(major == 10, DANET_E_ARCH, "device compute capability %d.x, need 10.x (sm_100a)", major);
   return DANET_OK;
 }
+
+// profiling aid: one thread stores %globaltimer (ns) -- lets a host script reconstruct the timeline of a
+// multi-stream CUDA graph, where CUDA events cannot be read back
+__global__ void timestamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
+extern "C" int danet_timestamp(unsigned long long* slot, void* stream) {
+  DANET_REQUIRE(slot, DANET_E_ARG, "timestamp: null pointer");
+  timestamp_kernel<<<1, 1, 0, danet::as_stream(stream)>>>(slot);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}

@@ -177,12 +177,14 @@ lstm_tc_kernel(const LstmTcParams p) {
     float c[UPT];
 #pragma unroll
     for (int uu = 0; uu < UPT; ++uu) c[uu] = 0.f;
-    float pre_next[4][UPT];
-    auto load_pre = [&](int s) {
+    // input projections are fetched TWO steps ahead: they do not depend on the recurrence, and under the
+    // stream-group schedule other groups' GEMMs saturate L2, stretching global latency beyond one step
+    float pre_q[2][4][UPT];
+    auto load_pre = [&](int s, float (&dst)[4][UPT]) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int uu = 0; uu < UPT; ++uu) pre_next[g][uu] = 0.f;
+        for (int uu = 0; uu < UPT; ++uu) dst[g][uu] = 0.f;
       if (valid && s < T) {
         const int to = dir ? T - 1 - s : s;
         const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
@@ -190,15 +192,16 @@ lstm_tc_kernel(const LstmTcParams p) {
         for (int g = 0; g < 4; ++g) {
           if (UPT == 4) {
             const float4 v = __ldcg(reinterpret_cast<const float4*>(q + g * H));
-            pre_next[g][0] = v.x; pre_next[g][1] = v.y; pre_next[g][UPT - 2] = v.z; pre_next[g][UPT - 1] = v.w;
+            dst[g][0] = v.x; dst[g][1] = v.y; dst[g][UPT - 2] = v.z; dst[g][UPT - 1] = v.w;
           } else {
             const float2 v = __ldcg(reinterpret_cast<const float2*>(q + g * H));
-            pre_next[g][0] = v.x; pre_next[g][1] = v.y;
+            dst[g][0] = v.x; dst[g][1] = v.y;
           }
         }
       }
     };
-    load_pre(0);
+    load_pre(0, pre_q[0]);
+    load_pre(1, pre_q[1]);
     const int outw = p.n_dir * H;
     float* xw = sXch + m * kXchLd;
     const uint32_t stage_off = sw64_offset(bl, ub);      // UPT contiguous bf16: units ub.. of utterance bl
@@ -208,8 +211,12 @@ lstm_tc_kernel(const LstmTcParams p) {
 #pragma unroll
       for (int uu = 0; uu < UPT; ++uu)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) a[uu][g] = pre_next[g][uu];
-      load_pre(s + 1);
+        for (int g = 0; g < 4; ++g) a[uu][g] = pre_q[0][g][uu];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int uu = 0; uu < UPT; ++uu) pre_q[0][g][uu] = pre_q[1][g][uu];
+      load_pre(s + 2, pre_q[1]);
       DANET_PROF(3);
       if (s > 0) {
         mbar_wait(acc_full, (s - 1) & 1);

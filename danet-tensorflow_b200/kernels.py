@@ -52,6 +52,19 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+_timeline = None      # (int64 device tensor, list of labels) while tools/timeline.py records
+
+
+def stamp(label):
+    """profiling aid: record %globaltimer on the current stream (no-op unless a timeline is being recorded)"""
+    if _timeline is None:
+        return
+    buf, labels = _timeline
+    i = len(labels)
+    labels.append(label)
+    _lib.check(_lib.load().danet_timestamp(C.c_void_p(buf.data_ptr() + 8 * i), _stream()), 'timestamp')
+
+
 def num_frames(n_samples):
     """T = ceil(N/64) + 1 (scipy.signal.stft padding as used at app/utils.py:117-122)"""
     t = _lib.load().danet_stft_num_frames(int(n_samples))

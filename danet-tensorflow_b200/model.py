@@ -105,7 +105,10 @@ class Model(object):
         if self._stagger_pending:          # see separate(): the next stream group may start now
             self._stagger_pending = False
             self._stagger_event = torch.cuda.current_stream().record_event()
-        return K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
+        K.stamp('%s gemm' % name)
+        out = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
+        K.stamp('%s lstm' % name)
+        return out
 
     # ---------------------------------------------------------------- training step (row a16)
     def _lyr_bilstm_train(self, name, s_x, hdim, weights):
@@ -300,8 +303,10 @@ class Model(object):
         else:
             mix_pwr = None
         embed = self.encoder(logmag)
+        K.stamp('proj')
         embed_flat = embed.view(B, T * F, -1)
         attrs = self.infer_estimator(embed, s_embed_flat=embed_flat)
+        K.stamp('attractor')
         out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=('sep',))
         return out['sep']
 
@@ -325,15 +330,19 @@ class Model(object):
             out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=self.device)
 
         def run(lo, hi):
+            K.stamp('g%d start' % lo)
             w = wav[lo:hi]
             if not w.is_cuda:
                 w = w.to(self.device, non_blocking=True)
             mix, logmag = K.stft(w, want_logmag=True)
+            K.stamp('g%d stft' % lo)
             sep = self.infer(mix, logmag=logmag)
+            K.stamp('g%d mask' % lo)
             if out.is_cuda:
                 K.istft(sep, out=out[lo:hi])
             else:
                 out[lo:hi].copy_(K.istft(sep), non_blocking=True)
+            K.stamp('g%d end' % lo)
 
         if groups <= 1:
             run(0, B)

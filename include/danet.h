@@ -42,6 +42,8 @@ int         danet_version(void);
 const char* danet_last_error_string(void);
 /* 0 if the current device is compute capability 10.x, DANET_E_ARCH otherwise */
 int         danet_check_device(void);
+/* profiling aid: a 1-thread kernel on `stream` stores %globaltimer (ns) into *slot (device memory) */
+int         danet_timestamp(unsigned long long* slot, void* stream);
 
 /* ---- K1  STFT front end -------------------------------------------------
  * replaces scipy.signal.stft as called at app/utils.py:117-122,

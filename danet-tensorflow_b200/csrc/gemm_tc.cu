@@ -26,9 +26,9 @@ static inline int pad_k(int K) { return (K + kTK - 1) / kTK * kTK; }
 
 // ---- operand split --------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int Kp,
+split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int Kp, long long lo_row,
                   __nv_bfloat16* __restrict__ out) {
-  // out[0..M) = hi rows, out[M..2M) = lo rows, each Kp wide
+  // out[0..M) = hi rows, out[lo_row..lo_row+M) = lo rows, each Kp wide
   const long long total = (long long)M * (Kp / 2);
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int m = (int)(i / (Kp / 2)), k = (int)(i % (Kp / 2)) * 2;
@@ -38,7 +38,7 @@ split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int 
     split_bf16(x0, h0, l0);
     split_bf16(x1, h1, l1);
     *reinterpret_cast<__nv_bfloat162*>(out + (size_t)m * Kp + k) = __nv_bfloat162(h0, h1);
-    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(M + m) * Kp + k) = __nv_bfloat162(l0, l1);
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(lo_row + m) * Kp + k) = __nv_bfloat162(l0, l1);
   }
 }
 
@@ -48,7 +48,7 @@ split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int 
 // [B,T,*] tensor (optionally shifted by one step) with a [T,B,*] one.
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N, int Kp, int perm_T, int shift,
-                       __nv_bfloat16* __restrict__ out) {
+                       long long lo_row, __nv_bfloat16* __restrict__ out) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -73,7 +73,7 @@ split_transpose_kernel(const float* __restrict__ W, long long ldw, int K, int N,
       __nv_bfloat16 h, l;
       split_bf16(tile[tx][r], h, l);
       out[(size_t)n * Kp + k] = h;
-      out[(size_t)(N + n) * Kp + k] = l;
+      out[(size_t)(lo_row + n) * Kp + k] = l;
     }
   }
 }
@@ -256,41 +256,30 @@ struct GemmOperand {
   int shift;     // with perm_T: time shift of the source row, zero filled
 };
 
-static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloat16* out, cudaStream_t stream) {
+static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloat16* out, long long lo_row,
+                         cudaStream_t stream) {
   if (op.trans == 0) {
     const long long total = (long long)R * (Kp / 2);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op.ptr, op.ld, R, K, Kp, out);
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op.ptr, op.ld, R, K, Kp, lo_row, out);
   } else {
     dim3 g(Kp / 32, (R + 31) / 32);
-    split_transpose_kernel<<<g, 256, 0, stream>>>(op.ptr, op.ld, K, R, Kp, op.perm_T, op.shift, out);
+    split_transpose_kernel<<<g, 256, 0, stream>>>(op.ptr, op.ld, K, R, Kp, op.perm_T, op.shift, lo_row, out);
   }
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
 
-// C[M,N] (ldc) (+)= A'[M,K] * B'[K,N] (+ bias), A' / B' described by GemmOperand
-int gemm_tc(const GemmOperand& A, const GemmOperand& B, const float* bias, float* C, long long ldc, int M, int N,
-            int K, int out_perm_T, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  DANET_REQUIRE(workspace, DANET_E_ARG, "gemm: the tcgen05 backend needs a workspace");
-  DANET_REQUIRE(workspace_bytes >= linear_tc_workspace_bytes(M, N, K), DANET_E_WORKSPACE,
-                "gemm: workspace %zu < %zu", workspace_bytes, linear_tc_workspace_bytes(M, N, K));
+// the product on operands that are already split: A2 [2M, Kp], B2 [2N, Kp] bf16 (hi rows, then lo rows)
+int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float* bias, float* C, long long ldc,
+                  int M, int N, int K, int out_perm_T, int accumulate, cudaStream_t stream) {
   DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "gemm: C and bias must be 16-byte aligned");
+  DANET_REQUIRE(aligned16(A2) && aligned16(B2), DANET_E_ALIGN, "gemm: split operands must be 16-byte aligned");
   const int Kp = pad_k(K);
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
-  __nv_bfloat16* A2 = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* B2 = reinterpret_cast<__nv_bfloat16*>(ws + ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024);
-  int rc = split_operand(A, M, K, Kp, A2, stream);
-  if (rc) return rc;
-  // B' is [K,N]: "own index" N; stored [K,N] means rows = K, i.e. the transposing split
-  GemmOperand Bt = B;
-  Bt.trans = B.trans ? 0 : 1;
-  rc = split_operand(Bt, N, K, Kp, B2, stream);
-  if (rc) return rc;
   CUtensorMap map_a, map_b;
-  rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
+  int rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
   if (rc) return rc;
   rc = make_tensor_map_bf16(&map_b, B2, 2ll * N, Kp, kTN);
   if (rc) return rc;
@@ -329,6 +318,26 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& B, const float* bias, float
   return DANET_OK;
 }
 
+// C[M,N] (ldc) (+)= A'[M,K] * B'[K,N] (+ bias), A' / B' described by GemmOperand
+int gemm_tc(const GemmOperand& A, const GemmOperand& B, const float* bias, float* C, long long ldc, int M, int N,
+            int K, int out_perm_T, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DANET_REQUIRE(workspace, DANET_E_ARG, "gemm: the tcgen05 backend needs a workspace");
+  DANET_REQUIRE(workspace_bytes >= linear_tc_workspace_bytes(M, N, K), DANET_E_WORKSPACE,
+                "gemm: workspace %zu < %zu", workspace_bytes, linear_tc_workspace_bytes(M, N, K));
+  const int Kp = pad_k(K);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* A2 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* B2 = reinterpret_cast<__nv_bfloat16*>(ws + ((size_t)2 * M * Kp * 2 + 1023) / 1024 * 1024);
+  int rc = split_operand(A, M, K, Kp, A2, M, stream);
+  if (rc) return rc;
+  // B' is [K,N]: "own index" N; stored [K,N] means rows = K, i.e. the transposing split
+  GemmOperand Bt = B;
+  Bt.trans = B.trans ? 0 : 1;
+  rc = split_operand(Bt, N, K, Kp, B2, N, stream);
+  if (rc) return rc;
+  return gemm_tc_split(A2, B2, bias, C, ldc, M, N, K, out_perm_T, accumulate, stream);
+}
+
 int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, float* C,
                   int M, int N, int K, int time_major_T, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream) {
@@ -361,4 +370,32 @@ extern "C" int danet_gemm(const float* A, long long lda, int transA, int permA_T
   GemmOperand a = {A, lda, transA ? 1 : 0, permA_T, shiftA}, b = {B, ldb, transB ? 1 : 0, 0, 0};
   return gemm_tc(a, b, bias, C, ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, workspace, workspace_bytes,
                  as_stream(stream));
+}
+
+extern "C" size_t danet_split_operand_bytes(int rows, int K) {
+  if (rows < 1 || K < 1) return 256;
+  return (size_t)2 * rows * pad_k(K) * 2;
+}
+
+extern "C" int danet_split_operand(const float* X, long long ld, int stored_k_major_rows, int rows, int K,
+                                   void* out_bf16, int row0, int rows_total, void* stream) {
+  DANET_REQUIRE(X && out_bf16, DANET_E_ARG, "split_operand: null pointer");
+  DANET_REQUIRE(rows >= 1 && K >= 1 && row0 >= 0 && rows_total >= row0 + rows, DANET_E_SHAPE,
+                "split_operand: rows %d K %d row0 %d rows_total %d", rows, K, row0, rows_total);
+  DANET_REQUIRE(aligned16(out_bf16), DANET_E_ALIGN, "split_operand: out must be 16-byte aligned");
+  const int Kp = pad_k(K);
+  GemmOperand op = {X, ld, stored_k_major_rows ? 1 : 0, 0, 0};
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16) + (size_t)row0 * Kp;
+  return split_operand(op, rows, K, Kp, out, rows_total, as_stream(stream));
+}
+
+extern "C" int danet_gemm_split(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M,
+                                int N, int K, int out_perm_T, int accumulate, void* stream) {
+  DANET_REQUIRE(A2 && B2 && C, DANET_E_ARG, "gemm_split: null pointer");
+  DANET_REQUIRE(M >= 0 && N >= 1 && K >= 1 && ldc >= N, DANET_E_SHAPE, "gemm_split: M %d N %d K %d ldc %lld", M, N, K, ldc);
+  DANET_REQUIRE(out_perm_T >= 0 && (out_perm_T == 0 || M % out_perm_T == 0), DANET_E_SHAPE,
+                "gemm_split: M %d is not a multiple of out_perm_T %d", M, out_perm_T);
+  if (M == 0) return DANET_OK;
+  return gemm_tc_split(reinterpret_cast<const __nv_bfloat16*>(A2), reinterpret_cast<const __nv_bfloat16*>(B2), bias, C,
+                       ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, as_stream(stream));
 }

@@ -11,9 +11,9 @@
 
 namespace danet {
 
-int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out,
-                float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H, void* workspace,
-                size_t workspace_bytes, cudaStream_t stream);
+int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
+                float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir, int T, int B,
+                int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
 
 constexpr int kU = 8;      // hidden units per CTA
@@ -31,7 +31,8 @@ struct LstmSeqParams {
   long long ldw;
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
-  float* gates_seq;        // nullable [n_dir][T][B][4H] post-activation [g|i|f|o]; may alias pre
+  float* gates_seq;        // nullable, indexed like pre: post-activation [g|i|f|o]; may alias pre
+  long long pre_dir, pre_row;   // element strides of pre: dir*pre_dir + (t*B + b)*pre_row + gate*H + unit
   int* counters;           // [n_dir][n_bt_total]
   int n_dir, T, B, H;
   int bt0;                 // first batch tile of this launch
@@ -78,7 +79,7 @@ lstm_seq_kernel(LstmSeqParams p) {
   auto load_pre = [&](int s, float (&dst)[4]) {
     if (valid && khalf == 0 && s < T) {
       const int to = dir ? T - 1 - s : s;
-      const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+      const float* q = p.pre + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
 #pragma unroll
       for (int g = 0; g < 4; ++g) dst[g] = __ldcg(q + g * H);
     }
@@ -139,7 +140,7 @@ lstm_seq_kernel(LstmSeqParams p) {
       __stcg(p.out + ((size_t)b * T + to) * outw + dir * H + unit, h);
       if (p.cell_seq) p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit] = c;
       if (p.gates_seq) {
-        float* gs = p.gates_seq + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+        float* gs = p.gates_seq + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
         gs[0] = g; gs[H] = ig; gs[2 * H] = fg; gs[3 * H] = og;
       }
     }
@@ -164,8 +165,9 @@ extern "C" size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H) {
   return simt > tc ? simt : tc;
 }
 
-extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
-                                  float* out, float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H,
+extern "C" int danet_lstm_seq_fwd(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                                  const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
+                                  float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
                                   void* workspace, size_t workspace_bytes, int backend,
                                   void* stream) {
   DANET_REQUIRE(pre && host_Wh && out && workspace, DANET_E_ARG, "lstm_seq: null pointer");
@@ -175,13 +177,21 @@ extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh,
                 "lstm_seq: T %d B %d H %d (multiple of 4) ldw %lld", T, B, H, ldw);
   DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq: backend %d", backend);
   DANET_REQUIRE(aligned16(out), DANET_E_ALIGN, "lstm_seq: out must be 16-byte aligned");
+  if (pre_dir_stride == 0 && pre_row_stride == 0) {       // default layout [n_dir][T][B][4H]
+    pre_row_stride = 4ll * H;
+    pre_dir_stride = (long long)T * B * 4 * H;
+  }
+  DANET_REQUIRE(pre_row_stride >= 4ll * H && pre_row_stride % 4 == 0 && pre_dir_stride % 4 == 0, DANET_E_SHAPE,
+                "lstm_seq: pre strides %lld / %lld", pre_dir_stride, pre_row_stride);
+  DANET_REQUIRE(backend == 1 || !out_split, DANET_E_ARG, "lstm_seq: out_split is produced by the tcgen05 backend only");
   DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
                 "lstm_seq: workspace %zu < %zu", workspace_bytes,
                 danet_lstm_seq_workspace_bytes(n_dir, B, H));
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
   if (backend == 1)
-    return lstm_tc_fwd(pre, host_Wh, ldw, out, cell_seq, gates_seq, n_dir, T, B, H, workspace, workspace_bytes, st);
+    return lstm_tc_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, out, cell_seq, gates_seq, out_split, out_split_kp,
+                       n_dir, T, B, H, workspace, workspace_bytes, st);
 
   const size_t smem = lstm_smem_bytes(H);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: H %d needs %zu B of shared memory", H, smem);
@@ -204,6 +214,7 @@ extern "C" int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh,
   p.out = out;
   p.cell_seq = cell_seq;
   p.gates_seq = gates_seq;
+  p.pre_dir = pre_dir_stride; p.pre_row = pre_row_stride;
   p.counters = reinterpret_cast<int*>(workspace);
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
   p.n_bt_total = n_bt;

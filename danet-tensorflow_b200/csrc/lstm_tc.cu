@@ -45,7 +45,10 @@ struct LstmTcParams {
   long long ldw;
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
-  float* gates_seq;        // nullable [n_dir][T][B][4H] post-activation [g|i|f|o]; may alias pre
+  float* gates_seq;        // nullable, indexed like pre: post-activation [g|i|f|o]; may alias pre
+  __nv_bfloat16* out_split;  // nullable [2][B*T][out_kp]: the hidden sequence as bf16 hi rows then lo rows,
+  int out_kp;                //   i.e. the next layer's tensor-core A operand, ready made
+  long long pre_dir, pre_row;   // element strides of pre: address = dir*pre_dir + (t*B + b)*pre_row + gate*H + unit
   int n_dir, T, B, H;
   long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
 };
@@ -187,7 +190,7 @@ lstm_tc_kernel(const LstmTcParams p) {
         for (int uu = 0; uu < UPT; ++uu) dst[g][uu] = 0.f;
       if (valid && s < T) {
         const int to = dir ? T - 1 - s : s;
-        const float* q = p.pre + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+        const float* q = p.pre + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (UPT == 4) {
@@ -247,11 +250,11 @@ lstm_tc_kernel(const LstmTcParams p) {
         a[uu][1] = ig; a[uu][2] = fg; a[uu][3] = og;           // post-activation gates, kept for training
       }
       DANET_PROF(7);
+      __nv_bfloat16 hi[UPT], lo[UPT];
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu) split_bf16(h[uu], hi[uu], lo[uu]);
       if (s < T - 1) {
         // my units of h_s as bf16 hi/lo into the staging K-block (already UMMA layout)
-        __nv_bfloat16 hi[UPT], lo[UPT];
-#pragma unroll
-        for (int uu = 0; uu < UPT; ++uu) split_bf16(h[uu], hi[uu], lo[uu]);
         // staged once for the peers, and written straight into this CTA's own B operand (a bulk copy whose
         // destination is the issuing CTA is not a remote access; the own slice needs no transport at all)
         uint8_t* st = sStage + (s & 1) * kHBlock;
@@ -275,8 +278,19 @@ lstm_tc_kernel(const LstmTcParams p) {
         asm volatile("bar.arrive 1, %0;" ::"r"(kEpiThreads + 32 * ncta) : "memory");
         DANET_PROF(8);
       }
+      if (valid && p.out_split) {
+        __nv_bfloat16* oh = p.out_split + ((size_t)b * T + to) * p.out_kp + dir * H + unit;
+        __nv_bfloat16* ol = oh + (size_t)B * T * p.out_kp;
+        if (UPT == 4) {
+          *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[UPT - 2], hi[UPT - 1]));
+          *reinterpret_cast<uint2*>(ol) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[UPT - 2], lo[UPT - 1]));
+        } else {
+          *reinterpret_cast<uint32_t*>(oh) = pack_bf16(hi[0], hi[1]);
+          *reinterpret_cast<uint32_t*>(ol) = pack_bf16(lo[0], lo[1]);
+        }
+      }
       if (valid && p.gates_seq) {
-        float* gs = p.gates_seq + (((size_t)dir * T + to) * B + b) * 4 * H + unit;
+        float* gs = p.gates_seq + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (UPT == 4) *reinterpret_cast<float4*>(gs + g * H) = make_float4(a[0][g], a[1][g], a[UPT - 2][g], a[UPT - 1][g]);
@@ -324,8 +338,13 @@ lstm_tc_kernel(const LstmTcParams p) {
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// The kernel needs ~55 KB but asks for the whole SM's shared memory: the recurrence is latency-bound, and a
+// co-resident CTA of another stream's kernel (attractor, mask, splits ...) would steal issue slots and
+// shared-memory bandwidth from the step's critical path.
 static size_t lstm_tc_smem_bytes(int ncta) {
-  return (size_t)(2 * ncta + 2) * kHBlock + (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
+  const size_t need = (size_t)(2 * ncta + 2) * kHBlock + (kRows * kXchLd + 2) * sizeof(float) + 64 + 1024;
+  const size_t whole_sm = 227 * 1024;
+  return need > whole_sm ? need : whole_sm;
 }
 
 template <int NB>
@@ -354,8 +373,8 @@ size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
 
 bool lstm_tc_supported(int H) { return H % 4 == 0 && (H + kUnits - 1) / kUnits <= kMaxCta; }
 
-int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
-                float* gates_seq, int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
+                float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
@@ -372,6 +391,16 @@ int lstm_tc_fwd(const float* pre, const float* const* host_Wh, long long ldw, fl
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
   p.ldw = ldw; p.out = out; p.cell_seq = cell_seq; p.gates_seq = gates_seq;
+  p.pre_dir = pre_dir; p.pre_row = pre_row;
+  p.out_split = reinterpret_cast<__nv_bfloat16*>(out_split);
+  p.out_kp = out_kp;
+  if (out_split) {
+    DANET_REQUIRE(out_kp >= n_dir * H && out_kp % 64 == 0 && aligned16(out_split), DANET_E_SHAPE,
+                  "lstm_seq: out_split needs a 16-byte aligned buffer with row length %d >= %d, multiple of 64", out_kp, n_dir * H);
+    if (out_kp > n_dir * H)      // zero the K padding of both halves once
+      DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,
+                                   (size_t)2 * B * T, stream));
+  }
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.

@@ -225,17 +225,22 @@ def _req_strided(t, name):
     return t
 
 
-def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_gates=False):
+def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_gates=False, interleaved=False,
+             want_split=False):
     """
     pre [n_dir,T,B,4H]; w_list = the reference's stacked [I+H,4H] matrices, one per direction
     (recurrent rows start at `in_dim`) -> hidden [B,T,n_dir*H] (+ cell [n_dir,T,B,H]).
     keep_gates: the post-activation gates [g|i|f|o] overwrite `pre` in place (training).
+    interleaved: `pre` is [T,B,n_dir,4H] (one product for both directions) instead of [n_dir,T,B,4H].
+    want_split: also return the hidden sequence as a ready-made tensor-core operand (split_rows layout).
     [main.py:76-132; app/ops.py:139-147; app/modules.py:120-137]
     """
     pre = _req(pre, 'pre', dim=4)
     n_dir = len(w_list)
-    if tuple(pre.shape) != (n_dir, T, B, 4 * H):
-        raise ValueError('lstm_seq: pre is %s, expected %s' % (tuple(pre.shape), (n_dir, T, B, 4 * H)))
+    want_shape = (T, B, n_dir, 4 * H) if interleaved else (n_dir, T, B, 4 * H)
+    if tuple(pre.shape) != want_shape:
+        raise ValueError('lstm_seq: pre is %s, expected %s' % (tuple(pre.shape), want_shape))
+    dir_stride, row_stride = (4 * H, n_dir * 4 * H) if interleaved else (0, 0)
     ptrs = (C.c_void_p * n_dir)()
     keep = []
     for d, w in enumerate(w_list):
@@ -254,11 +259,41 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
         be = DEFAULT_BACKEND if H <= TC_LSTM_MAX_H else 0
     else:
         be = backend
-    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), ptrs, 4 * H, _p(out), _p(cell), _p(pre) if keep_gates else None,
-                                      n_dir, T, B, H, _p(ws),
+    out_split, kp = None, 0
+    if want_split:
+        kp = (n_dir * H + 63) // 64 * 64
+        out_split = torch.empty((2, B * T, kp), dtype=torch.bfloat16, device=pre.device)
+    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), dir_stride, row_stride, ptrs, 4 * H, _p(out), _p(cell),
+                                      _p(pre) if keep_gates else None, _p(out_split), kp, n_dir, T, B, H, _p(ws),
                                       ws.numel(), be, _stream()), 'lstm_seq')
     _count()
+    if want_split:
+        return out, out_split
     return (out, cell) if keep_cell else out
+
+
+def split_operand(x, k_major_rows, out=None, row0=0, rows_total=None):
+    """fp32 [rows,K] (k_major_rows=False) or [K,rows] (True) -> bf16 [2*rows_total, Kp] hi/lo operand"""
+    x = _req_strided(x, 'x')
+    rows, Kd = (x.shape[1], x.shape[0]) if k_major_rows else (x.shape[0], x.shape[1])
+    rows_total = rows if rows_total is None else rows_total
+    kp = (Kd + 63) // 64 * 64
+    if out is None:
+        out = torch.empty((2 * rows_total, kp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().danet_split_operand(_p(x), x.stride(0), int(k_major_rows), rows, Kd, _p(out), row0, rows_total,
+                                               _stream()), 'split_operand')
+    _count()
+    return out
+
+
+def gemm_split(a2, b2, m, n, k, bias=None, out=None, out_perm_T=0, accumulate=False):
+    """C[m,n] (+)= A2 @ B2^T (+ bias) on operands already in the split bf16 layout"""
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a2.device)
+    _lib.check(_lib.load().danet_gemm_split(_p(a2), _p(b2), _p(bias), _p(out), out.stride(0), m, n, k, int(out_perm_T),
+                                            int(accumulate), _stream()), 'gemm_split')
+    _count()
+    return out
 
 
 def _embed_flat(embed):

@@ -33,6 +33,8 @@ class Model(object):
         self._stagger_event = None
         self._streams = []
         self._graphs = {}
+        self._packed = {}                 # weights pre-split for the tensor cores (dropped whenever they change)
+        self._last_split = None           # (hidden sequence, its split copy) handed from layer to layer
         self._tape = None                 # training: saved activations per recurrent layer
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
         self.step_count = 0
@@ -54,6 +56,7 @@ class Model(object):
 
     def load_params(self, params):
         """Take weights by reference name (numpy arrays or tensors); the role of main.py:201-206"""
+        self._packed = {}
         for k, v in params.items():
             t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
             t = t.to(device=self.device, dtype=torch.float32).contiguous()
@@ -98,6 +101,8 @@ class Model(object):
         Wb, Bb = self._lstm_vars(name + '_bwd', I, hdim, w_init, b_init)
         if self._tape is not None:
             return self._lyr_bilstm_train(name, s_x, hdim, (Wf, Bf, Wb, Bb))
+        if K.DEFAULT_BACKEND == 1 and hdim <= K.TC_LSTM_MAX_H:
+            return self._lyr_bilstm_packed(name, s_x, hdim, (Wf, Bf, Wb, Bb))
         x2 = s_x.reshape(B * T, I)
         pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
         K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
@@ -109,6 +114,42 @@ class Model(object):
         out = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim)
         K.stamp('%s lstm' % name)
         return out
+
+    # ---------------------------------------------------------------- inference fast path
+    def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
+        """Same arithmetic as lyr_bilstm with the operand traffic trimmed: the two directions' input weights are
+        split to bf16 hi/lo ONCE and kept side by side (one product, N = 8H, instead of two), and the layer input
+        arrives already split from the previous layer's recurrent kernel, so the dense layer is a single launch."""
+        Wf, Bf, Wb, Bb = weights
+        B, T, I = s_x.shape
+        ent = self._packed.get(name)
+        if ent is None:
+            N = 8 * hdim
+            w2 = K.split_operand(Wf[:I], True, rows_total=N, row0=0)
+            K.split_operand(Wb[:I], True, out=w2, rows_total=N, row0=4 * hdim)
+            ent = (w2, torch.cat([Bf, Bb]))
+            self._packed[name] = ent
+        w2, bias2 = ent
+        prev = self._last_split
+        a2 = prev[1] if prev is not None and prev[0] is s_x else K.split_operand(s_x.reshape(B * T, I), False)
+        pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=T).view(T, B, 2, 4 * hdim)
+        if self._stagger_pending:          # see separate(): the next stream group may start now
+            self._stagger_pending = False
+            self._stagger_event = torch.cuda.current_stream().record_event()
+        K.stamp('%s gemm' % name)
+        out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True)
+        K.stamp('%s lstm' % name)
+        self._last_split = (out, out_split)
+        return out
+
+    def dense(self, name, x2, W, bias=None):
+        """x2 [M,K] @ W (+ bias) with the weight operand split once and cached (inference)"""
+        if self._tape is not None or K.DEFAULT_BACKEND != 1:
+            return K.linear(x2, W, bias)
+        w2 = self._packed.get(name)
+        if w2 is None:
+            w2 = self._packed[name] = K.split_operand(W, True)
+        return K.gemm_split(K.split_operand(x2, False), w2, x2.shape[0], W.shape[1], W.shape[0], bias=bias)
 
     # ---------------------------------------------------------------- training step (row a16)
     def _lyr_bilstm_train(self, name, s_x, hdim, weights):
@@ -131,6 +172,7 @@ class Model(object):
         for k in names:
             offs[k] = total
             total += (self.params[k].numel() + 63) // 64 * 64          # 256-byte aligned views
+        self._packed = {}
         flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         grad = torch.zeros_like(flat)
         for k in names:
@@ -195,6 +237,8 @@ class Model(object):
         """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then the registered optimiser (app/ozers.py), one fused
         launch over the flat parameter buffer"""
         self.step_count += 1
+        self._packed = {}
+        self._graphs = {}                 # captured graphs hold the old packed weights
         f = self._flat
         opt = hparams.get_optimizer()(hparams.LR)
         if opt['kind'] == 'adam':

@@ -141,7 +141,7 @@ class _RecurrentEncoder(Encoder):
         odim = x.shape[-1]
         E = hparams.EMBED_SIZE
         W = model.get_variable('%s/output/W' % self.name, [odim, F * E], _uniform(-1.85, 1.85))
-        v = K.linear(x.view(B * T, odim), W)                       # modules.py:249-255, no bias
+        v = model.dense('%s/output/W' % self.name, x.view(B * T, odim), W)   # modules.py:249-255, no bias
         s_out = v.view(B, T, F, E)
         if hparams.DEBUG:
             self.debug_fetches['embed'] = s_out

@@ -105,21 +105,40 @@ int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shift
                float* C, long long ldc, int M, int N, int K, int out_perm_T, int accumulate,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* operands that do not change between calls (weights) or that a producer kernel can emit directly
+ * (danet_lstm_seq_fwd out_split) skip the split pass of danet_gemm / danet_linear_fwd:
+ *   danet_split_operand: X -> bf16 [2*rows_total, Kp] (hi rows [0,rows_total), lo rows after them), filling
+ *     rows row0 .. row0+rows; Kp = K rounded up to 64, zero padded.  stored_k_major_rows = 0: X is
+ *     [rows, K] (ld); 1: X is [K, rows] (ld), e.g. a [K,N] weight matrix.  Concatenating two weight
+ *     matrices (row0) yields one product for both LSTM directions.
+ *   danet_gemm_split: C[M,N] (ldc) (+)= A2 * B2^T (+ bias) on split operands A2 [2M,Kp], B2 [2N,Kp]. */
+size_t danet_split_operand_bytes(int rows, int K);
+int danet_split_operand(const float* X, long long ld, int stored_k_major_rows, int rows, int K,
+                        void* out_bf16, int row0, int rows_total, void* stream);
+int danet_gemm_split(const void* A2, const void* B2, const float* bias, float* C, long long ldc,
+                     int M, int N, int K, int out_perm_T, int accumulate, void* stream);
+
 /* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------
  * replaces Model.lyr_lstm (main.py:76-132: tf.scan from zero state) over
  * ops.lyr_lstm_flat (app/ops.py:139-147: gates [cand|i|f|o], candidate WITHOUT tanh,
  * c' = i*g + f*c, h' = o*tanh(c')) and _lyr_bilstm (app/modules.py:120-137).
- *   pre   [n_dir][T][B][4H]  x_t*Wx + bias for every step (danet_linear_fwd output);
- *         direction 1 is indexed by ORIGINAL time (it walks t = T-1 .. 0)
+ *   pre   x_t*Wx + bias for every step (danet_linear_fwd output), element (dir, t, b, j) at
+ *         dir*pre_dir_stride + (t*B + b)*pre_row_stride + j; both strides 0 = the default
+ *         [n_dir][T][B][4H]; (4H, 8H) = [T][B][n_dir][4H], the output of ONE product with the two
+ *         directions' weights side by side.  Direction 1 is indexed by ORIGINAL time
+ *         (it walks t = T-1 .. 0)
  *   Wh    n_dir pointers to the recurrent rows W[I:I+H, 0:4H] (row stride ldw)
  *   out   [B][T][n_dir*H]  hidden sequence, fwd in [0,H), bwd in [H,2H) (un-reversed)
  *   cell_seq (nullable) [n_dir][T][B][H] cell states kept for the backward pass
- *   gates_seq (nullable) [n_dir][T][B][4H] post-activation gates [g|i|f|o] kept for the
+ *   gates_seq (nullable) indexed like pre: post-activation gates [g|i|f|o] kept for the
  *         backward pass; MAY ALIAS pre (each element is read once, then overwritten)
+ *   out_split (nullable, backend 1) [2][B*T][out_split_kp] bf16: the hidden sequence again as hi
+ *         rows then lo rows, K padded with zeros -- the next layer's danet_gemm_split operand
  * backend: 0 = fp32 SIMT cooperative kernel, 1 = tcgen05 cluster kernel. */
 size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H);
-int danet_lstm_seq_fwd(const float* pre, const float* const* host_Wh, long long ldw,
-                       float* out, float* cell_seq, float* gates_seq, int n_dir, int T, int B, int H,
+int danet_lstm_seq_fwd(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                       const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
+                       float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
                        void* workspace, size_t workspace_bytes, int backend, void* stream);
 /* backward through time (TF autodiff of the tf.scan at main.py:125-131): walks the sequence in
  * reverse, dh = d_out_t + da_{t+1} Wh^T, and overwrites `gates` ([g|i|f|o] from the forward) with

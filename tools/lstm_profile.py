@@ -16,7 +16,7 @@ ptrs = (C.c_void_p * 2)(*[w.data_ptr() + I * 4 * H * 4 for w in Ws])
 out = torch.empty(B, T, 2 * H, device='cuda')
 ws = torch.zeros(1 << 20, dtype=torch.uint8, device='cuda')
 for _ in range(2):
-    rc = lib.danet_lstm_seq_fwd(C.c_void_p(pre.data_ptr()), ptrs, 4 * H, C.c_void_p(out.data_ptr()), None, None, 2, T, B, H,
+    rc = lib.danet_lstm_seq_fwd(C.c_void_p(pre.data_ptr()), 0, 0, ptrs, 4 * H, C.c_void_p(out.data_ptr()), None, None, None, 0, 2, T, B, H,
                                 C.c_void_p(ws.data_ptr()), ws.numel(), 1, None)
     assert rc == 0, lib.danet_last_error_string()
 torch.cuda.synchronize()

@@ -69,6 +69,14 @@ center_apply_kernel(const float* __restrict__ x, long long n_per, const float* _
     yb[i] = xb[i] - m;
 }
 
+__global__ void mean_final_kernel(const float* __restrict__ part, int B, long long n_per, float* __restrict__ mean) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float t = 0.f;
+  for (int p = 0; p < kCenterParts; ++p) t += part[b * kCenterParts + p];     // same order as center_apply_kernel
+  mean[b] = t / (float)n_per;
+}
+
 __global__ void __launch_bounds__(256)
 leaky_relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float leak) {
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -146,6 +154,17 @@ extern "C" int danet_center_fwd(const float* x, int B, long long n_per, float* y
   long long cap = max(1, (num_sms() * 8 + B - 1) / B);
   if (gx > cap) gx = cap;
   center_apply_kernel<<<dim3((unsigned)gx, B), 256, 0, as_stream(stream)>>>(x, n_per, workspace, y);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_mean_fwd(const float* x, int B, long long n_per, float* mean, float* workspace, void* stream) {
+  DANET_REQUIRE(x && mean && workspace, DANET_E_ARG, "mean: null pointer");
+  DANET_REQUIRE(B >= 0 && B <= 65535 && n_per >= 1, DANET_E_SHAPE, "mean: B %d n_per %lld", B, n_per);
+  if (B == 0) return DANET_OK;
+  center_partial_kernel<<<dim3(kCenterParts, B), 256, 0, as_stream(stream)>>>(x, n_per, workspace);
+  DANET_LAUNCH_CHECK();
+  mean_final_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(workspace, B, n_per, mean);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }

@@ -85,6 +85,9 @@ struct GemmParams {
   long long ldc;
   int M, N, n_kblocks, T, nb;   // T > 0: logical row b*T+t is stored at row t*nb+b
   int accumulate;               // C += instead of C =
+  const float* row_mu;          // nullable [M / rows_per_mu]: C[row, n] -= row_mu[row / rows_per_mu] * col_s[n]
+  const float* col_s;           //   (mean-centring of A folded into the epilogue: (x - mu) W = x W - mu colsum(W))
+  int rows_per_mu;
   int kb_per_split;             // K blocks per blockIdx.z (split-K: partial sums are added atomically)
   int atomic;                   // 1 when gridDim.z > 1
 };
@@ -169,6 +172,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const size_t orow = p.T > 0 ? (size_t)(row % p.T) * p.nb + row / p.T : (size_t)row;
     float* crow = p.C + orow * p.ldc;
     const bool vec = (p.ldc & 3) == 0;
+    const float mu = (p.row_mu && row_ok) ? __ldg(p.row_mu + row / p.rows_per_mu) : 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < kTN; c0 += 32) {
       if (n0 + c0 >= p.N) break;                       // warp-uniform
@@ -186,6 +190,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.row_mu) {
+              const float4 ss = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + j));
+              o.x = fmaf(-mu, ss.x, o.x); o.y = fmaf(-mu, ss.y, o.y); o.z = fmaf(-mu, ss.z, o.z); o.w = fmaf(-mu, ss.w, o.w);
+            }
             if (p.bias) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -200,7 +208,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
-            if (n < p.N) crow[n] = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f) + (p.accumulate ? crow[n] : 0.f);
+            if (n < p.N)
+              crow[n] = v[j] - (p.row_mu ? mu * __ldg(p.col_s + n) : 0.f) + (p.bias ? __ldg(p.bias + n) : 0.f) +
+                        (p.accumulate ? crow[n] : 0.f);
           }
         }
       }
@@ -274,7 +284,8 @@ static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloa
 
 // the product on operands that are already split: A2 [2M, Kp], B2 [2N, Kp] bf16 (hi rows, then lo rows)
 int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float* bias, float* C, long long ldc,
-                  int M, int N, int K, int out_perm_T, int accumulate, cudaStream_t stream) {
+                  int M, int N, int K, int out_perm_T, int accumulate, cudaStream_t stream, const float* row_mu = nullptr,
+                  const float* col_s = nullptr, int rows_per_mu = 1) {
   DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "gemm: C and bias must be 16-byte aligned");
   DANET_REQUIRE(aligned16(A2) && aligned16(B2), DANET_E_ALIGN, "gemm: split operands must be 16-byte aligned");
   const int Kp = pad_k(K);
@@ -287,6 +298,7 @@ int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float*
   p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.n_kblocks = Kp / kTK;
   p.T = out_perm_T; p.nb = out_perm_T > 0 ? M / out_perm_T : 0;
   p.accumulate = accumulate;
+  p.row_mu = row_mu; p.col_s = col_s; p.rows_per_mu = rows_per_mu > 0 ? rows_per_mu : 1;
   DANET_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
   dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
   DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "gemm: M %d too large", M);
@@ -295,7 +307,7 @@ int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float*
   {
     const int tiles = (int)(grid.x * grid.y), sms = num_sms();
     int splits = 1;
-    if (tiles * 2 <= sms && p.n_kblocks >= 16) {
+    if (tiles * 2 <= sms && p.n_kblocks >= 16 && !row_mu) {
       splits = sms / tiles;
       const int max_splits = p.n_kblocks / 8;
       if (splits > max_splits) splits = max_splits;
@@ -389,13 +401,16 @@ extern "C" int danet_split_operand(const float* X, long long ld, int stored_k_ma
   return split_operand(op, rows, K, Kp, out, rows_total, as_stream(stream));
 }
 
-extern "C" int danet_gemm_split(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M,
-                                int N, int K, int out_perm_T, int accumulate, void* stream) {
+extern "C" int danet_gemm_split(const void* A2, const void* B2, const float* bias, const float* row_mu,
+                                const float* col_s, int rows_per_mu, float* C, long long ldc, int M, int N, int K,
+                                int out_perm_T, int accumulate, void* stream) {
   DANET_REQUIRE(A2 && B2 && C, DANET_E_ARG, "gemm_split: null pointer");
   DANET_REQUIRE(M >= 0 && N >= 1 && K >= 1 && ldc >= N, DANET_E_SHAPE, "gemm_split: M %d N %d K %d ldc %lld", M, N, K, ldc);
   DANET_REQUIRE(out_perm_T >= 0 && (out_perm_T == 0 || M % out_perm_T == 0), DANET_E_SHAPE,
                 "gemm_split: M %d is not a multiple of out_perm_T %d", M, out_perm_T);
+  DANET_REQUIRE(!row_mu || (col_s && rows_per_mu >= 1 && aligned16(col_s)), DANET_E_ARG,
+                "gemm_split: row_mu needs col_s (16-byte aligned) and rows_per_mu >= 1");
   if (M == 0) return DANET_OK;
   return gemm_tc_split(reinterpret_cast<const __nv_bfloat16*>(A2), reinterpret_cast<const __nv_bfloat16*>(B2), bias, C,
-                       ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, as_stream(stream));
+                       ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, as_stream(stream), row_mu, col_s, rows_per_mu);
 }

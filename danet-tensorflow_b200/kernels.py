@@ -136,6 +136,18 @@ def center(x, out=None):
     return y
 
 
+def mean(x):
+    """per-utterance mean over all other axes -> [B] (the statistic of `center`)"""
+    x = _req(x, 'x')
+    B = x.shape[0]
+    out = torch.empty((B,), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    ws = _ws(lib.danet_center_workspace_bytes(B), x.device)
+    _lib.check(lib.danet_mean_fwd(_p(x), B, x[0].numel() if B else 1, _p(out), _p(ws), _stream()), 'mean')
+    _count(2)
+    return out
+
+
 def leaky_relu(x, leak=0., inplace=True):
     """max(x*leak, x) [app/ops.py:93-107]"""
     x = _req(x, 'x')
@@ -286,12 +298,15 @@ def split_operand(x, k_major_rows, out=None, row0=0, rows_total=None):
     return out
 
 
-def gemm_split(a2, b2, m, n, k, bias=None, out=None, out_perm_T=0, accumulate=False):
-    """C[m,n] (+)= A2 @ B2^T (+ bias) on operands already in the split bf16 layout"""
+def gemm_split(a2, b2, m, n, k, bias=None, out=None, out_perm_T=0, accumulate=False, row_mu=None, col_s=None,
+               rows_per_mu=1):
+    """C[m,n] (+)= A2 @ B2^T (+ bias) (- row_mu[row // rows_per_mu] * col_s[n]) on operands already in the split
+    bf16 layout"""
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=a2.device)
-    _lib.check(_lib.load().danet_gemm_split(_p(a2), _p(b2), _p(bias), _p(out), out.stride(0), m, n, k, int(out_perm_T),
-                                            int(accumulate), _stream()), 'gemm_split')
+    _lib.check(_lib.load().danet_gemm_split(_p(a2), _p(b2), _p(bias), _p(row_mu), _p(col_s), int(rows_per_mu), _p(out),
+                                            out.stride(0), m, n, k, int(out_perm_T), int(accumulate), _stream()),
+               'gemm_split')
     _count()
     return out
 

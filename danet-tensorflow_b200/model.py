@@ -101,7 +101,7 @@ class Model(object):
         Wb, Bb = self._lstm_vars(name + '_bwd', I, hdim, w_init, b_init)
         if self._tape is not None:
             return self._lyr_bilstm_train(name, s_x, hdim, (Wf, Bf, Wb, Bb))
-        if K.DEFAULT_BACKEND == 1 and hdim <= K.TC_LSTM_MAX_H:
+        if self.USE_PACKED and K.DEFAULT_BACKEND == 1 and hdim <= K.TC_LSTM_MAX_H:
             return self._lyr_bilstm_packed(name, s_x, hdim, (Wf, Bf, Wb, Bb))
         x2 = s_x.reshape(B * T, I)
         pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
@@ -116,6 +116,9 @@ class Model(object):
         return out
 
     # ---------------------------------------------------------------- inference fast path
+    USE_PACKED = True          # one product per layer on cached pre-split weights + operands emitted by the LSTM
+    USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
+
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
         """Same arithmetic as lyr_bilstm with the operand traffic trimmed: the two directions' input weights are
         split to bf16 hi/lo ONCE and kept side by side (one product, N = 8H, instead of two), and the layer input
@@ -141,6 +144,20 @@ class Model(object):
         K.stamp('%s lstm' % name)
         self._last_split = (out, out_split)
         return out
+
+    def centered_projection(self, name, x, W):
+        """(x - mean_b(x)) @ W for x [B,T,K] (app/modules.py:244-255) as ONE product on the operand the last
+        recurrent layer already emitted: (x - mu) W = x W - mu colsum(W), the rank-1 term applied in the epilogue.
+        Returns None when the fast path does not apply."""
+        prev = self._last_split
+        if not self.USE_CENTER_FOLD or self._tape is not None or K.DEFAULT_BACKEND != 1 or prev is None or prev[0] is not x:
+            return None
+        ent = self._packed.get(name)
+        if ent is None:
+            ent = self._packed[name] = (K.split_operand(W, True), K.colsum(W))
+        w2, col_s = ent
+        B, T, Kd = x.shape
+        return K.gemm_split(prev[1], w2, B * T, W.shape[1], Kd, row_mu=K.mean(x), col_s=col_s, rows_per_mu=T)
 
     def dense(self, name, x2, W, bias=None):
         """x2 [M,K] @ W (+ bias) with the weight operand split once and cached (inference)"""

@@ -135,13 +135,15 @@ class _RecurrentEncoder(Encoder):
                 x = _lyr_bilstm('%s/lstm%d' % (self.name, l), model, x, hdim, w_init, b_init, s_dropout_keep)
             else:
                 x = model.lyr_lstm('%s/lstm%d' % (self.name, l), x, hdim, w_init=w_init, b_init=b_init)
-        x = K.center(x)                                            # modules.py:244-245 / :181-182
-        if model._tape is not None:
-            model._tape.append(dict(centered=x))
         odim = x.shape[-1]
         E = hparams.EMBED_SIZE
         W = model.get_variable('%s/output/W' % self.name, [odim, F * E], _uniform(-1.85, 1.85))
-        v = model.dense('%s/output/W' % self.name, x.view(B * T, odim), W)   # modules.py:249-255, no bias
+        v = model.centered_projection('%s/output/W' % self.name, x, W)    # centring folded into the product
+        if v is None:
+            x = K.center(x)                                        # modules.py:244-245 / :181-182
+            if model._tape is not None:
+                model._tape.append(dict(centered=x))
+            v = model.dense('%s/output/W' % self.name, x.view(B * T, odim), W)   # modules.py:249-255, no bias
         s_out = v.view(B, T, F, E)
         if hparams.DEBUG:
             self.debug_fetches['embed'] = s_out

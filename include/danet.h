@@ -69,6 +69,9 @@ int danet_mix_features_fwd(const float* src_c64, int B, int C, int TF,
 size_t danet_center_workspace_bytes(int B);
 int danet_center_fwd(const float* x, int B, long long n_per, float* y,
                      float* workspace, void* stream);
+/* the per-utterance means alone (same workspace): lets the centring be folded into the next dense layer's
+ * epilogue, (x - mu) W = x W - mu colsum(W)  -- see danet_gemm_split(row_mu, col_s) */
+int danet_mean_fwd(const float* x, int B, long long n_per, float* mean, float* workspace, void* stream);
 
 /* leaky ReLU of the `toy` encoder: y = max(x*leak, x) (app/ops.py:93-107); y may alias x */
 int danet_leaky_relu_fwd(const float* x, float* y, long long n, float leak, void* stream);
@@ -111,11 +114,14 @@ int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shift
  *     rows row0 .. row0+rows; Kp = K rounded up to 64, zero padded.  stored_k_major_rows = 0: X is
  *     [rows, K] (ld); 1: X is [K, rows] (ld), e.g. a [K,N] weight matrix.  Concatenating two weight
  *     matrices (row0) yields one product for both LSTM directions.
- *   danet_gemm_split: C[M,N] (ldc) (+)= A2 * B2^T (+ bias) on split operands A2 [2M,Kp], B2 [2N,Kp]. */
+ *   danet_gemm_split: C[M,N] (ldc) (+)= A2 * B2^T (+ bias) on split operands A2 [2M,Kp], B2 [2N,Kp];
+ *     row_mu (nullable [M / rows_per_mu]) and col_s [N] subtract row_mu[row / rows_per_mu] * col_s[n]
+ *     in the epilogue (mean-centring of A, app/modules.py:244-245, folded into the projection). */
 size_t danet_split_operand_bytes(int rows, int K);
 int danet_split_operand(const float* X, long long ld, int stored_k_major_rows, int rows, int K,
                         void* out_bf16, int row0, int rows_total, void* stream);
-int danet_gemm_split(const void* A2, const void* B2, const float* bias, float* C, long long ldc,
+int danet_gemm_split(const void* A2, const void* B2, const float* bias, const float* row_mu,
+                     const float* col_s, int rows_per_mu, float* C, long long ldc,
                      int M, int N, int K, int out_perm_T, int accumulate, void* stream);
 
 /* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------

@@ -216,21 +216,27 @@ def main():
     out_host = torch.empty((B, N_SPK, 64 * T), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    # instrument the dominant kernel (recurrent LSTM) with events on the launching stream
-    lstm_events = []
-    raw_lstm = K.lstm_seq
+    # instrument our kernels with events on the launching stream (used in the eager pass only)
+    kernel_events = {}
 
-    def timed_lstm(*a, **kw):
-        if not timed_lstm.on:
-            return raw_lstm(*a, **kw)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = raw_lstm(*a, **kw)
-        e1.record()
-        lstm_events.append((e0, e1))
-        return r
-    timed_lstm.on = False
-    K.lstm_seq = timed_lstm
+    class Timed(object):
+        on = False
+
+    def instrument(name):
+        raw = getattr(K, name)
+
+        def timed(*a, **kw):
+            if not Timed.on:
+                return raw(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = raw(*a, **kw)
+            e1.record()
+            kernel_events.setdefault(name, []).append((e0, e1))
+            return r
+        setattr(K, name, timed)
+    for nm in ('lstm_seq', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'gemm_split', 'split_operand', 'mean'):
+        instrument(nm)
 
     def barrier():
         if world > 1:
@@ -270,11 +276,12 @@ def main():
     # the same K steps once more, eagerly on one stream, with CUDA events around every launch of the dominant
     # kernel (events cannot be read back from inside a replayed graph) and our launch counter running
     K.launches = 0
-    timed_lstm.on = True
+    Timed.on = True
     ms_eager = timed_loop(lambda: model.separate(wav_dev, groups=1), args.steps)
-    timed_lstm.on = False
+    Timed.on = False
     launches = K.launches
-    lstm_ms = [a.elapsed_time(b) for a, b in lstm_events]
+    per_kernel = {k: [a.elapsed_time(b) for a, b in v] for k, v in kernel_events.items()}
+    lstm_ms = per_kernel.get('lstm_seq', [])
     clocks = sampler.stop()
 
     # ---- extra: the training step of the same config (forward + backward + gradient all-reduce + clip/Adam)
@@ -322,6 +329,37 @@ def main():
                 'note': 'algorithmic fp32 flops 2*n_dir*B*H*4H*T; the kernel is bound by the latency of T '
                         'dependent steps, not by tensor throughput'}
 
+    # the other kernels of the step against their own rooflines (algorithmic bytes / flops from DESIGN.md section 6)
+    hbm = peaks.get('hbm_gbs', 6650.)
+    TF, E = T * 129, EMBED
+
+    def avg_ms(name):
+        v = per_kernel.get(name, [])
+        return float(np.mean(v)) if v else None
+    kernels = []
+    for name, bound, work, note in (
+            ('stft', 'hbm', B * (4. * N_SAMPLES + 12. * TF), 'wav in, complex spectrum + log-magnitude out'),
+            ('attractor_anchor', 'hbm', B * 4. * TF * E, 'one read of the embedding (fp32 SIMT products: 336 MAC per bin)'),
+            ('mask_cmul', 'hbm', B * (4. * TF * E + 8. * TF + 8. * N_SPK * TF), 'embedding + mixture in, separated spectra out'),
+            ('istft', 'hbm', B * N_SPK * (8. * TF + 4. * 64 * T), 'spectra in, waveforms out'),
+            ('gemm_split', 'tensor', None, 'hoisted input projections (N = 2400) and the output projection (N = 2580), bf16x3')):
+        ms = avg_ms(name)
+        if ms is None:
+            continue
+        if bound == 'hbm':
+            ach = work / (ms * 1e-3) / 1e9
+            kernels.append({'kernel': name, 'bound': 'hbm', 'ms_per_launch': ms, 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+                            'frac': ach / hbm, 'note': note})
+        else:
+            n_calls = len(per_kernel[name]) // args.steps
+            flops = 2. * B * T * (129 * 2400 + 3 * 600 * 2400 + 600 * 2580)          # logical fp32 flops per step
+            tot_ms = ms * n_calls
+            ach = flops / (tot_ms * 1e-3) / 1e12
+            kernels.append({'kernel': name, 'bound': 'tensor', 'ms_per_step': tot_ms, 'launches_per_step': n_calls,
+                            'achieved': ach, 'issued': 3 * ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+                            'frac_issued': 3 * ach / peak_tf,
+                            'note': note + '; "issued" counts the 3 bf16 products behind every fp32-grade product'})
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -340,7 +378,7 @@ def main():
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
-        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train,
+        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train, 'kernels': kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

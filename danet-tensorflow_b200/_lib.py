@@ -35,6 +35,10 @@ PROTOTYPES = {
     'danet_lstm_seq_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
     'danet_lstm_seq_fwd': (c_i, [c_f, c_ll, c_ll, C.POINTER(C.c_void_p), c_ll, c_f, c_f, c_f, c_v, c_i,
                                  c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
+    'danet_lstm_pack_wh_bytes': (c_sz, [c_i, c_i]),
+    'danet_lstm_pack_wh': (c_i, [C.POINTER(C.c_void_p), c_ll, c_i, c_i, c_v, c_sz, c_v]),
+    'danet_lstm_seq_fwd_packed': (c_i, [c_f, c_ll, c_ll, C.POINTER(C.c_void_p), c_ll, c_v, c_f, c_f, c_f, c_v, c_i,
+                                        c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
     'danet_split_operand_bytes': (c_sz, [c_i, c_i]),
     'danet_split_operand': (c_i, [c_f, c_ll, c_i, c_i, c_i, c_v, c_i, c_i, c_v]),
     'danet_gemm_split': (c_i, [c_v, c_v, c_f, c_f, c_f, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_v]),

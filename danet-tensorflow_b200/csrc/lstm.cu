@@ -12,9 +12,13 @@
 namespace danet {
 
 int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
+                const void* wh_packed,
                 float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir, int T, int B,
-                int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
+size_t lstm_tc_pack_bytes(int n_dir, int H);
+int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed, cudaStream_t stream);
+bool lstm_tc_supported(int H);
 
 constexpr int kU = 8;      // hidden units per CTA
 constexpr int kBt = 16;    // utterances per CTA
@@ -165,17 +169,56 @@ extern "C" size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H) {
   return simt > tc ? simt : tc;
 }
 
+extern "C" size_t danet_lstm_pack_wh_bytes(int n_dir, int H) {
+  if (n_dir < 1 || H < 4 || !lstm_tc_supported(H)) return 0;
+  return lstm_tc_pack_bytes(n_dir, H);
+}
+
+extern "C" int danet_lstm_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed,
+                                  size_t packed_bytes, void* stream) {
+  DANET_REQUIRE(host_Wh && packed, DANET_E_ARG, "lstm_pack_wh: null pointer");
+  DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_pack_wh: n_dir %d", n_dir);
+  for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_pack_wh: null Wh[%d]", d);
+  DANET_REQUIRE(H >= 4 && H % 4 == 0 && ldw >= 4ll * H, DANET_E_SHAPE, "lstm_pack_wh: H %d ldw %lld", H, ldw);
+  DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE, "lstm_pack_wh: H %d is outside the tcgen05 backend's range", H);
+  DANET_REQUIRE(packed_bytes >= lstm_tc_pack_bytes(n_dir, H), DANET_E_WORKSPACE, "lstm_pack_wh: buffer %zu < %zu",
+                packed_bytes, lstm_tc_pack_bytes(n_dir, H));
+  return lstm_tc_pack_wh(host_Wh, ldw, n_dir, H, packed, as_stream(stream));
+}
+
+static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                             const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
+                             float* cell_seq, float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T,
+                             int B, int H, void* workspace, size_t workspace_bytes, int backend, void* stream);
+
 extern "C" int danet_lstm_seq_fwd(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                                   const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
                                   float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
-                                  void* workspace, size_t workspace_bytes, int backend,
-                                  void* stream) {
+                                  void* workspace, size_t workspace_bytes, int backend, void* stream) {
+  return lstm_seq_fwd_impl(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, nullptr, out, cell_seq, gates_seq,
+                           out_split, out_split_kp, n_dir, T, B, H, workspace, workspace_bytes, backend, stream);
+}
+
+extern "C" int danet_lstm_seq_fwd_packed(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                                         const float* const* host_Wh, long long ldw, const void* wh_packed,
+                                         float* out, float* cell_seq, float* gates_seq, void* out_split,
+                                         int out_split_kp, int n_dir, int T, int B, int H, void* workspace,
+                                         size_t workspace_bytes, int backend, void* stream) {
+  DANET_REQUIRE(!wh_packed || backend >= 1, DANET_E_ARG, "lstm_seq: wh_packed is read by the tcgen05 backends only");
+  return lstm_seq_fwd_impl(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, cell_seq, gates_seq,
+                           out_split, out_split_kp, n_dir, T, B, H, workspace, workspace_bytes, backend, stream);
+}
+
+static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                             const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
+                             float* cell_seq, float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T,
+                             int B, int H, void* workspace, size_t workspace_bytes, int backend, void* stream) {
   DANET_REQUIRE(pre && host_Wh && out && workspace, DANET_E_ARG, "lstm_seq: null pointer");
   DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_seq: n_dir %d", n_dir);
   for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_seq: null Wh[%d]", d);
   DANET_REQUIRE(T >= 0 && B >= 0 && H >= 4 && H % 4 == 0 && ldw >= 4ll * H, DANET_E_SHAPE,
                 "lstm_seq: T %d B %d H %d (multiple of 4) ldw %lld", T, B, H, ldw);
-  DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq: backend %d", backend);
+  DANET_REQUIRE(backend >= 0 && backend <= 2, DANET_E_ARG, "lstm_seq: backend %d", backend);
   DANET_REQUIRE(aligned16(out), DANET_E_ALIGN, "lstm_seq: out must be 16-byte aligned");
   if (pre_dir_stride == 0 && pre_row_stride == 0) {       // default layout [n_dir][T][B][4H]
     pre_row_stride = 4ll * H;
@@ -183,15 +226,15 @@ extern "C" int danet_lstm_seq_fwd(const float* pre, long long pre_dir_stride, lo
   }
   DANET_REQUIRE(pre_row_stride >= 4ll * H && pre_row_stride % 4 == 0 && pre_dir_stride % 4 == 0, DANET_E_SHAPE,
                 "lstm_seq: pre strides %lld / %lld", pre_dir_stride, pre_row_stride);
-  DANET_REQUIRE(backend == 1 || !out_split, DANET_E_ARG, "lstm_seq: out_split is produced by the tcgen05 backend only");
+  DANET_REQUIRE(backend >= 1 || !out_split, DANET_E_ARG, "lstm_seq: out_split is produced by the tcgen05 backends only");
   DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
                 "lstm_seq: workspace %zu < %zu", workspace_bytes,
                 danet_lstm_seq_workspace_bytes(n_dir, B, H));
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
-  if (backend == 1)
-    return lstm_tc_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, out, cell_seq, gates_seq, out_split, out_split_kp,
-                       n_dir, T, B, H, workspace, workspace_bytes, st);
+  if (backend >= 1)
+    return lstm_tc_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, cell_seq, gates_seq, out_split, out_split_kp,
+                       n_dir, T, B, H, backend == 2, workspace, workspace_bytes, st);
 
   const size_t smem = lstm_smem_bytes(H);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: H %d needs %zu B of shared memory", H, smem);

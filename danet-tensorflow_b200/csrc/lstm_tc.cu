@@ -18,6 +18,7 @@
 // mbarrier.  No global-memory round trip and no cluster-wide barrier sits on the T-step
 // critical path.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -42,6 +43,7 @@ constexpr int kAccCols = 32;          // accumulator: columns [0,16) of the firs
 struct LstmTcParams {
   const float* pre;        // [n_dir][T][B][4H]
   const float* Wh[2];      // recurrent rows [H][4H] (row stride ldw)
+  const uint32_t* Wh_packed;   // nullable: pre-split rows in TMEM order (danet_lstm_pack_wh), read instead of Wh
   long long ldw;
   float* out;              // [B][T][n_dir*H]
   float* cell_seq;         // nullable [n_dir][T][B][H]
@@ -338,6 +340,370 @@ lstm_tc_kernel(const LstmTcParams p) {
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ================================================================================================
+// Second generation of the 8-utterances-per-cluster kernel (the default whenever every cluster is
+// co-resident).  Same decomposition and transport as above; the T-step critical path is shorter.
+// Measured anatomy of the first generation (profiles/r01_lstm_phase_cycles_v4.txt): the MMA phase is bound by
+// streaming the A operand out of tensor memory (~14 cycles per fresh 128x16 bf16 tile, 5 when the tile repeats), the
+// exchange of h by the ~17 B/cycle an SM can move through DSMEM while sending and receiving.  So:
+//   * HF = 0 (backend 1, "bf16x3"): hi and lo of h share ONE B tile along N: a K-block is [lo atom | hi atom | zero
+//     atom] (8 rows x 64 B each, SWIZZLE_64B, SBO = 512), A_hi x [lo | hi] puts hi*lo in accumulator columns 0-7 and
+//     hi*hi in 8-15, A_lo x [hi | 0] adds lo*hi to columns 0-7: 40 MMAs per step instead of 60;
+//   * HF = 1 (backend 2): h travels as ONE fp16 value (|h| < 1: 11 significant bits, 2^-12 relative rounding) and
+//     multiplies the bf16 hi/lo pair of Wh: 40 MMAs, and HALF the DSMEM bytes (512 B per peer per step).  Measured
+//     effect on the embedding (tools/precision_study.py): 1e-4 max-norm relative, against 2e-6 for HF = 0 and the
+//     1e-3 gate;
+//   * 8 epilogue warps (two per TMEM lane quadrant, 4 utterances each), one (unit, utterance) pair per thread;
+//   * the gate-row -> (unit, utterance) regrouping is a 4x4 butterfly of warp shuffles among the 4 lanes that hold
+//     one unit's gates (no shared-memory round trip);
+//   * the two sigmoids feeding the cell share one reciprocal, as do the output gate and tanh: 6 MUFU ops per pair
+//     instead of 8;
+//   * Wh arrives pre-split (danet_lstm_pack_wh) through one bulk copy per CTA: prologue 45k -> 6k cycles.
+constexpr int kEpi2Warps = 8;
+constexpr int kEpi2Threads = 32 * kEpi2Warps;
+constexpr int kThreads2 = kEpi2Threads + 32 + 32 * kMaxCta;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t umma_desc_k_sw64_sbo512(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+// kind::f16 with fp16 A (TMEM) and fp16 B (smem): the two formats of one instruction may not differ
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// (x0, x1) -> packed bf16 pair of the high parts and of the residuals, two F2FP instead of four F2F
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t t0, float (&a)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(t0) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = __uint_as_float(r[i]);
+}
+// two 32x32b.x4 loads (columns c0.. and c1..) behind one wait
+__device__ __forceinline__ void tmem_ld_2x4(uint32_t t0, uint32_t t1, float (&a)[4], float (&b)[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(t0) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t1) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); }
+}
+
+template <int HF>
+__global__ void __launch_bounds__(kThreads2, 1)
+lstm_tc2_kernel(const LstmTcParams p) {
+  constexpr int NB = 8;
+  // one K-block (32 units) of the B operand: HF 0: [lo 512 | hi 512 | zero 512 | pad]; HF 1: [fp16 512 | zero 512]
+  constexpr int kBlk = HF ? 1024 : 2048;
+  constexpr uint32_t kSend = HF ? 512 : 1024;       // bytes per peer per step
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int ncta = gridDim.x;
+  const int rank = (int)cluster_ctarank();
+  const int bt = blockIdx.y, dir = blockIdx.z;
+  const int H = p.H, T = p.T, B = p.B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kMmaWarp = kEpi2Warps, kSend0 = kEpi2Warps + 1;
+
+  uint8_t* sH = smem;                                          // [2 buf][ncta][kBlk]
+  uint8_t* sStage = sH + 2 * ncta * kBlk;                      // [2][kSend]
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(sStage + 2 * kSend);
+  uint64_t* acc_full = h_full + 2;
+  uint64_t* w_full = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint8_t* sW = sStage + 2 * kSend + 64;                       // packed Wh slice, prologue only (16-byte aligned)
+
+  const int unit0 = rank * kUnits;
+  const int b0 = bt * NB;
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                       (tid == 0 || warp == kMmaWarp || warp == kSend0);
+  if (prof_on && tid == 0) p.prof[10] = clock64();
+
+  if (tid == 0) {
+    mbar_init(h_full + 0, ncta);
+    mbar_init(h_full + 1, ncta);
+    mbar_init(acc_full, 1);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    if (p.Wh_packed) {
+      const uint32_t bytes = (uint32_t)kRows * (uint32_t)(ncta * 32 + 4) * 4u;
+      // the packed buffer holds a bf16 image (backend 1) followed by an fp16 image (backend 2)
+      const size_t image = (size_t)p.n_dir * ncta * kRows * (size_t)(ncta * 32 + 4);
+      const uint32_t* src = p.Wh_packed + (HF ? image : 0) +
+                            ((size_t)dir * ncta + rank) * (size_t)kRows * (size_t)(ncta * 32 + 4);
+      mbar_arrive_expect_tx(w_full, bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sW)), "l"(src), "r"(bytes), "r"(smem_u32(w_full)) : "memory");
+    }
+  }
+  for (int i = tid; i < (2 * ncta * kBlk + 2 * (int)kSend) / 16; i += kThreads2)
+    reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc = tmem_base;
+  const uint32_t tmem_a_hi = tmem_base + kAccCols;
+  const uint32_t tmem_a_lo = tmem_a_hi + (uint32_t)ncta * 16;
+
+  // ---- one-time: this CTA's rows of Wh^T -> packed bf16 hi/lo in TMEM (lane = gate row 4*unit + gate) ----
+  if (warp < 4) {
+    const int m = tid, u = m >> 2, g = m & 3, unit = unit0 + u;
+    const bool unit_ok = unit < H;
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    if (p.Wh_packed) {
+      // pre-split rows (danet_lstm_pack_wh): [dir][rank][128 rows][ncta*16 hi words | ncta*16 lo words | 4 pad words].
+      // The whole 160 KB slice was fetched into shared memory by ONE bulk copy (issued by thread 0 above); the 16-byte
+      // row pad makes the per-lane row reads conflict-free.
+      const int rw = ncta * 32 + 4;
+      mbar_wait(w_full, 0);
+      const uint4* row = reinterpret_cast<const uint4*>(sW + (size_t)m * rw * 4);
+      for (int k0 = 0; k0 < ncta * 16; k0 += 8) {
+        const uint4 h0 = row[k0 >> 2], h1 = row[(k0 >> 2) + 1];
+        const uint4 l0 = row[(ncta * 16 + k0) >> 2], l1 = row[((ncta * 16 + k0) >> 2) + 1];
+        const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        tmem_st_32x8(tmem_a_hi + lane_sel + k0, hi);
+        tmem_st_32x8(tmem_a_lo + lane_sel + k0, lo);
+      }
+    } else {
+      const float* wcol = p.Wh[dir] + (size_t)g * H + unit;
+      for (int k0 = 0; k0 < ncta * 32; k0 += 16) {
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = (unit_ok && k0 + i < H) ? __ldg(wcol + (size_t)(k0 + i) * p.ldw) : 0.f;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (HF) split2_f16(w[2 * i], w[2 * i + 1], hi[i], lo[i]);
+          else split2_bf16(w[2 * i], w[2 * i + 1], hi[i], lo[i]);
+        }
+        tmem_st_32x8(tmem_a_hi + lane_sel + (k0 >> 1), hi);
+        tmem_st_32x8(tmem_a_lo + lane_sel + (k0 >> 1), lo);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync();
+  if (prof_on && tid == 0) p.prof[11] = clock64();
+
+  if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = HF ? umma_idesc_f16(kRows, kUmmaN) : umma_idesc_bf16(kRows, kUmmaN);
+      for (int s = 1; s < T; ++s) {
+        const int buf = (s - 1) & 1;
+        const uint64_t b0d = umma_desc_k_sw64_sbo512(smem_u32(sH + (size_t)buf * ncta * kBlk));
+        DANET_PROF(0);
+        mbar_wait(h_full + buf, ((s - 1) >> 1) & 1);
+        DANET_PROF(1);
+        tc_fence_after();
+#pragma unroll 2
+        for (int j = 0; j < ncta; ++j) {
+          // HF 0: rows 0-7 lo, rows 8-15 hi for A_hi; rows 0-7 hi, rows 8-15 zero for A_lo.  HF 1: [h | zero] for both.
+          const uint64_t b_first = b0d + (uint64_t)((j * kBlk) >> 4);
+          const uint64_t b_second = HF ? b_first : b_first + (uint64_t)(512 >> 4);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t ac = (uint32_t)(j * 16 + k * 8);
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_first + adv, idesc, (j | k) != 0);
+            umma_bf16_ts(tmem_acc, tmem_a_lo + ac, b_second + adv, idesc, 1);
+          }
+        }
+        umma_commit(acc_full);
+        DANET_PROF(2);
+      }
+    }
+  } else if (warp < kEpi2Warps) {
+    // ================= epilogue: TMEM lane 32*q + lane = 4*unit + gate; this warp's utterances 4*hw .. 4*hw+3 =====
+    const int q = warp & 3, hw = warp >> 2;
+    const int u = lane >> 2, g = lane & 3;
+    const int ul = 8 * q + u;                      // unit inside the CTA
+    const int bl = 4 * hw + g;                     // utterance inside the tile (after the butterfly)
+    const int b = b0 + bl, unit = unit0 + ul;
+    const bool valid = b < B && unit < H;
+    const bool g1 = (g & 1) != 0, g2 = (g & 2) != 0;
+    float c = 0.f;
+    float pre_q[2][4];
+    auto load_pre = [&](int s, float (&dst)[4]) {
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) dst[gg] = 0.f;
+      if (valid && s < T) {
+        const int to = dir ? T - 1 - s : s;
+        const float* qp = p.pre + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) dst[gg] = __ldcg(qp + gg * H);
+      }
+    };
+    load_pre(0, pre_q[0]);
+    load_pre(1, pre_q[1]);
+    const int outw = p.n_dir * H;
+    const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+    const uint32_t stage_off = sw64_offset(bl, ul & ~1);      // the (even, odd) unit pair of utterance bl: 4 bytes
+    const uint32_t stage_addr = smem_u32(sStage) + stage_off;
+    const uint32_t own_addr = smem_u32(sH + (size_t)rank * kBlk) + stage_off;
+    const bool odd = (u & 1) != 0;
+    constexpr float kL2e = 1.4426950408889634f;
+    for (int s = 0; s < T; ++s) {
+      const int to = dir ? T - 1 - s : s;
+      float a[4];
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) { a[gg] = pre_q[0][gg]; pre_q[0][gg] = pre_q[1][gg]; }
+      load_pre(s + 2, pre_q[1]);
+      DANET_PROF(3);
+      if (s > 0) {
+        mbar_wait(acc_full, (s - 1) & 1);
+        DANET_PROF(4);
+        tc_fence_after();
+        float sk[4];                                       // my gate row, utterances 4*hw + k
+        if (HF) {
+          tmem_ld_32x4(tmem_acc + lane_sel + 4 * hw, sk);
+        } else {
+          float v1[4];
+          tmem_ld_2x4(tmem_acc + lane_sel + 4 * hw, tmem_acc + lane_sel + 8 + 4 * hw, sk, v1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sk[k] += v1[k];
+        }
+        DANET_PROF(5);
+        tc_fence_before();
+        // stage 1 (lanes g, g^2): keep my half of the utterances, get the partner's gate for it
+        const float keep0 = g2 ? sk[2] : sk[0], keep1 = g2 ? sk[3] : sk[1];
+        const float r0 = __shfl_xor_sync(0xffffffffu, g2 ? sk[0] : sk[2], 2);
+        const float r1 = __shfl_xor_sync(0xffffffffu, g2 ? sk[1] : sk[3], 2);
+        // stage 2 (lanes g, g^1): keep utterance g, get gates g^1 and g^3 for it
+        const float mine = g1 ? keep1 : keep0, mine2 = g1 ? r1 : r0;
+        const float rA = __shfl_xor_sync(0xffffffffu, g1 ? keep0 : keep1, 1);
+        const float rB = __shfl_xor_sync(0xffffffffu, g1 ? r0 : r1, 1);
+        // gate x sits in slot g ^ x (0 mine, 1 rA, 2 mine2, 3 rB): two levels of selects, no branches
+        const float lo_e = g1 ? rA : mine, lo_o = g1 ? mine : rA;      // slots {0,1} for x even / odd
+        const float hi_e = g1 ? rB : mine2, hi_o = g1 ? mine2 : rB;    // slots {2,3}
+        a[0] += g2 ? hi_e : lo_e;
+        a[1] += g2 ? hi_o : lo_o;
+        a[2] += g2 ? lo_e : hi_e;
+        a[3] += g2 ? lo_o : hi_o;
+      }
+      DANET_PROF(6);
+      // c = sig(i)*g + sig(f)*c ; h = sig(o)*tanh(c)   (candidate WITHOUT tanh, app/ops.py:141-147)
+      const float ei = ex2_approx(-kL2e * fmaxf(a[1], -30.f));
+      const float ef = ex2_approx(-kL2e * fmaxf(a[2], -30.f));
+      const float eo = ex2_approx(-kL2e * fmaxf(a[3], -30.f));
+      const float pi = 1.f + ei, pf = 1.f + ef, po = 1.f + eo;
+      const float rif = rcp_approx(pi * pf);
+      const float ig = rif * pf, fg = rif * pi;
+      c = ig * a[0] + fg * c;
+      const float ec = ex2_approx(-2.f * kL2e * fabsf(c));
+      const float pc = 1.f + ec;
+      const float roc = rcp_approx(po * pc);
+      const float og = roc * pc;
+      const float th = copysignf((1.f - ec) * roc * po, c);
+      const float h = valid ? og * th : 0.f;
+      DANET_PROF(7);
+      // pair up with the neighbouring unit (lane ^ 4) so 16-bit values travel as 32-bit words
+      const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
+      const float he = odd ? hn : h, ho = odd ? h : hn;        // units (ul & ~1), (ul | 1)
+      uint32_t vh, vl;
+      if (!HF) split2_bf16(he, ho, vh, vl);
+      if (s < T - 1) {
+        if (!odd) {
+          const uint32_t st = stage_addr + (uint32_t)(s & 1) * kSend;
+          const uint32_t own = own_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
+          if (HF) {
+            const __half2 v16 = __floats2half2_rn(he, ho);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(&v16);
+            st_shared_u32(st, v);
+            st_shared_u32(own, v);
+          } else {
+            st_shared_u32(st, vl);
+            st_shared_u32(st + 512, vh);
+            st_shared_u32(own, vl);
+            st_shared_u32(own + 512, vh);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.arrive 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
+        DANET_PROF(8);
+      }
+      if (valid) {
+        if (odd && p.out_split) {
+          if (HF) split2_bf16(he, ho, vh, vl);
+          __nv_bfloat16* oh = p.out_split + ((size_t)b * T + to) * p.out_kp + dir * H + (unit - 1);
+          *reinterpret_cast<uint32_t*>(oh) = vh;
+          *reinterpret_cast<uint32_t*>(oh + (size_t)B * T * p.out_kp) = vl;
+        }
+        p.out[((size_t)b * T + to) * outw + dir * H + unit] = h;
+        if (p.cell_seq) p.cell_seq[(((size_t)dir * T + to) * B + b) * H + unit] = c;
+        if (p.gates_seq) {
+          float* gs = p.gates_seq + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
+          gs[0] = a[0]; gs[H] = ig; gs[2 * H] = fg; gs[3 * H] = og;
+        }
+      }
+    }
+  } else if (warp >= kSend0 && warp - kSend0 < ncta) {
+    // ================= sender warps: warp kSend0+i ships this CTA's slice of h_s to peer rank+i =================
+    const int peer = (rank + (warp - kSend0)) % ncta;
+    const uint32_t peer_dst = mapa(smem_u32(sH + (size_t)rank * kBlk), peer);
+    const uint32_t peer_bar = mapa(smem_u32(h_full), peer);
+    for (int s = 0; s + 1 < T; ++s) {
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
+      if (elect_one_sync()) {
+        if (peer == rank) {
+          mbar_arrive(h_full + (s & 1));
+        } else {
+          const uint32_t boff = (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
+          const uint32_t bar = peer_bar + (uint32_t)(s & 1) * 8;
+          mbar_arrive_expect_tx_cluster(bar, kSend);
+          dsmem_bulk_copy(peer_dst + boff, smem_u32(sStage + (s & 1) * kSend), kSend, bar);
+        }
+        DANET_PROF(9);
+      }
+      __syncwarp();
+    }
+  }
+  if (prof_on && tid == 0) p.prof[12] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+  if (prof_on && tid == 0) p.prof[13] = clock64();
+}
+
 // The kernel needs ~55 KB but asks for the whole SM's shared memory: the recurrence is latency-bound, and a
 // co-resident CTA of another stream's kernel (attractor, mask, splits ...) would steal issue slots and
 // shared-memory bandwidth from the step's critical path.
@@ -346,26 +712,35 @@ static size_t lstm_tc_smem_bytes(int ncta) {
   const size_t whole_sm = 227 * 1024;
   return need > whole_sm ? need : whole_sm;
 }
+static size_t lstm_tc2_packed_smem_bytes(int ncta) {
+  return (size_t)2 * ncta * 2048 + 2 * 1024 + 64 + (size_t)kRows * (ncta * 32 + 4) * 4 + 1024;
+}
+static bool lstm_tc2_packed_fits(int ncta) { return lstm_tc2_packed_smem_bytes(ncta) <= 227 * 1024; }
 
-template <int NB>
-static int launch_lstm_tc(const LstmTcParams& p, int ncta, cudaStream_t stream) {
-  const size_t smem = lstm_tc_smem_bytes(ncta);
-  DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ncta > 8)
-    DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ncta, (p.B + NB - 1) / NB, p.n_dir);
-  cfg.blockDim = dim3(kThreads);
+static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int threads, size_t smem, int ncta,
+                        cudaStream_t stream) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = ncta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DANET_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_kernel<NB>, p));
+}
+
+template <typename Kern>
+static int launch_cluster(Kern kern, const LstmTcParams& p, int ncta, int nb, int threads, cudaStream_t stream) {
+  const size_t smem = lstm_tc_smem_bytes(ncta);
+  DANET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ncta > 8) DANET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_cfg(cfg, attr, dim3(ncta, (p.B + nb - 1) / nb, p.n_dir), threads, smem, ncta, stream);
+  DANET_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return DANET_OK;
 }
 
@@ -373,14 +748,56 @@ size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
 
 bool lstm_tc_supported(int H) { return H % 4 == 0 && (H + kUnits - 1) / kUnits <= kMaxCta; }
 
+// ---- Wh -> the recurrent kernel's TMEM image, once per weight update ------------------------------------------
+// [image][dir][rank][128 rows m = 4*unit + gate][ncta*16 hi words | ncta*16 lo words | 4 pad words]; word j of a row
+// holds elements k = 2j (low half) and 2j+1 of Wh[k][gate*H + 32*rank + unit] as bf16 (image 0) or fp16 (image 1).
+__global__ void lstm_pack_wh_kernel(const float* W0, const float* W1, long long ldw, int H, int ncta, uint32_t* out) {
+  const int rank = blockIdx.x, dir = blockIdx.y, m = threadIdx.x;
+  const bool f16 = blockIdx.z != 0;                 // image 0: bf16 pairs (backend 1), image 1: fp16 pairs (backend 2)
+  out += (size_t)blockIdx.z * gridDim.y * ncta * kRows * (size_t)(ncta * 32 + 4);
+  const int unit = rank * kUnits + (m >> 2), g = m & 3;
+  const int rw = ncta * 32 + 4;
+  const float* W = dir ? W1 : W0;
+  uint32_t* row = out + (((size_t)dir * ncta + rank) * kRows + m) * (size_t)rw;
+  const bool unit_ok = unit < H;
+  for (int j = 0; j < ncta * 16; ++j) {
+    const int k = 2 * j;
+    const float w0 = (unit_ok && k < H) ? __ldg(W + (size_t)k * ldw + (size_t)g * H + unit) : 0.f;
+    const float w1 = (unit_ok && k + 1 < H) ? __ldg(W + (size_t)(k + 1) * ldw + (size_t)g * H + unit) : 0.f;
+    uint32_t hi, lo;
+    if (f16) split2_f16(w0, w1, hi, lo);
+    else split2_bf16(w0, w1, hi, lo);
+    row[j] = hi;
+    row[ncta * 16 + j] = lo;
+  }
+  for (int j = 0; j < 4; ++j) row[ncta * 32 + j] = 0u;
+}
+
+size_t lstm_tc_pack_bytes(int n_dir, int H) {
+  const int ncta = (H + kUnits - 1) / kUnits;
+  return (size_t)2 * n_dir * ncta * kRows * (size_t)(ncta * 32 + 4) * 4;      // bf16 image + fp16 image
+}
+
+int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed, cudaStream_t stream) {
+  DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE, "lstm_pack_wh: H %d is outside the tcgen05 backend's range", H);
+  DANET_REQUIRE(aligned16(packed), DANET_E_ALIGN, "lstm_pack_wh: packed must be 16-byte aligned");
+  const int ncta = (H + kUnits - 1) / kUnits;
+  lstm_pack_wh_kernel<<<dim3(ncta, n_dir, 2), kRows, 0, stream>>>(host_Wh[0], n_dir > 1 ? host_Wh[1] : host_Wh[0], ldw, H, ncta,
+                                                               reinterpret_cast<uint32_t*>(packed));
+  DANET_CUDA(cudaGetLastError());
+  return DANET_OK;
+}
+
 int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
-                float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                const void* wh_packed, float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir,
+                int T, int B, int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
                 "H <= %d (got %d); use backend 0", kMaxCta * kUnits, H);
   DANET_REQUIRE(aligned16(pre) && aligned16(out) && (!cell_seq || aligned16(cell_seq)), DANET_E_ALIGN,
                 "lstm_seq: pre/out/cell_seq must be 16-byte aligned");
+  DANET_REQUIRE(!wh_packed || aligned16(wh_packed), DANET_E_ALIGN, "lstm_seq: wh_packed must be 16-byte aligned");
   long long* prof = nullptr;
   if (getenv("DANET_LSTM_PROFILE") && workspace && workspace_bytes >= (size_t)T * kProfSlots * sizeof(long long)) {
     prof = reinterpret_cast<long long*>(workspace);
@@ -390,6 +807,7 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   p.pre = pre;
   p.Wh[0] = host_Wh[0];
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
+  p.Wh_packed = nullptr;
   p.ldw = ldw; p.out = out; p.cell_seq = cell_seq; p.gates_seq = gates_seq;
   p.pre_dir = pre_dir; p.pre_row = pre_row;
   p.out_split = reinterpret_cast<__nv_bfloat16*>(out_split);
@@ -405,31 +823,33 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
   const int clusters8 = n_dir * ((B + 7) / 8);
-  int resident = 0;
-  {
+  static int resident_cache[kMaxCta + 1] = {0};
+  int resident = resident_cache[ncta];
+  if (resident == 0) {
     const size_t smem = lstm_tc_smem_bytes(ncta);
-    DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DANET_CUDA(cudaFuncSetAttribute(lstm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ncta > 8)
-      DANET_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ncta, clusters8, 1);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
+      DANET_CUDA(cudaFuncSetAttribute(lstm_tc2_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ncta;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&resident, lstm_tc_kernel<8>, &cfg) != cudaSuccess) {
+    cluster_cfg(cfg, attr, dim3(ncta, clusters8, 1), kThreads2, smem, ncta, nullptr);
+    if (cudaOccupancyMaxActiveClusters(&resident, lstm_tc2_kernel<0>, &cfg) != cudaSuccess || resident <= 0) {
       cudaGetLastError();
       resident = num_sms() / (ncta + 2);
     }
+    resident_cache[ncta] = resident;
   }
   const char* force = getenv("DANET_LSTM_NB");
   const int nb = force ? atoi(force) : (clusters8 <= resident ? 8 : 16);
-  return nb == 8 ? launch_lstm_tc<8>(p, ncta, stream) : launch_lstm_tc<16>(p, ncta, stream);
+  // backend 2 (fp16 recurrent state) exists for the 8-per-cluster kernel only; a batch too large for that runs the
+  // (more exact) bf16x3 kernel with 16 utterances per cluster instead
+  if (nb != 8) return launch_cluster(lstm_tc_kernel<16>, p, ncta, 16, kThreads, stream);
+  const char* ver = getenv("DANET_LSTM_V");
+  if (ver && atoi(ver) == 1 && !h_fp16) return launch_cluster(lstm_tc_kernel<8>, p, ncta, 8, kThreads, stream);
+  if (wh_packed && lstm_tc2_packed_fits(ncta) && !getenv("DANET_LSTM_NOPACK"))
+    p.Wh_packed = reinterpret_cast<const uint32_t*>(wh_packed);
+  return h_fp16 ? launch_cluster(lstm_tc2_kernel<1>, p, ncta, 8, kThreads2, stream)
+                : launch_cluster(lstm_tc2_kernel<0>, p, ncta, 8, kThreads2, stream);
 }
 
 }  // namespace danet

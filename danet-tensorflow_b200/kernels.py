@@ -237,8 +237,26 @@ def _req_strided(t, name):
     return t
 
 
+def lstm_pack_wh(w_list, in_dim, H):
+    """recurrent rows of the stacked [I+H,4H] matrices -> the tcgen05 recurrent kernel's TMEM image (bf16 hi/lo),
+    or None when H is outside that backend's range.  Valid until the weights change."""
+    lib = _lib.load()
+    n_dir = len(w_list)
+    nbytes = lib.danet_lstm_pack_wh_bytes(n_dir, H)
+    if nbytes == 0:
+        return None
+    ptrs = (C.c_void_p * n_dir)()
+    for d, w in enumerate(w_list):
+        w = _req(w, 'W[%d]' % d, dim=2)
+        ptrs[d] = w.data_ptr() + in_dim * 4 * H * 4
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=w_list[0].device)
+    _lib.check(lib.danet_lstm_pack_wh(ptrs, 4 * H, n_dir, H, _p(packed), nbytes, _stream()), 'lstm_pack_wh')
+    _count()
+    return packed
+
+
 def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_gates=False, interleaved=False,
-             want_split=False):
+             want_split=False, wh_packed=None):
     """
     pre [n_dir,T,B,4H]; w_list = the reference's stacked [I+H,4H] matrices, one per direction
     (recurrent rows start at `in_dim`) -> hidden [B,T,n_dir*H] (+ cell [n_dir,T,B,H]).
@@ -275,9 +293,10 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
     if want_split:
         kp = (n_dir * H + 63) // 64 * 64
         out_split = torch.empty((2, B * T, kp), dtype=torch.bfloat16, device=pre.device)
-    _lib.check(lib.danet_lstm_seq_fwd(_p(pre), dir_stride, row_stride, ptrs, 4 * H, _p(out), _p(cell),
-                                      _p(pre) if keep_gates else None, _p(out_split), kp, n_dir, T, B, H, _p(ws),
-                                      ws.numel(), be, _stream()), 'lstm_seq')
+    _lib.check(lib.danet_lstm_seq_fwd_packed(_p(pre), dir_stride, row_stride, ptrs, 4 * H,
+                                             _p(wh_packed) if be == 1 else None, _p(out), _p(cell),
+                                             _p(pre) if keep_gates else None, _p(out_split), kp, n_dir, T, B, H,
+                                             _p(ws), ws.numel(), be, _stream()), 'lstm_seq')
     _count()
     if want_split:
         return out, out_split

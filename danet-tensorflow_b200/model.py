@@ -117,6 +117,10 @@ class Model(object):
 
     # ---------------------------------------------------------------- inference fast path
     USE_PACKED = True          # one product per layer on cached pre-split weights + operands emitted by the LSTM
+    # Inference carries h_{t-1} into the recurrent product as ONE fp16 value (C-ABI backend 2) instead of a bf16 hi/lo
+    # pair: half the DSMEM bytes per step, ~1e-4 max-norm deviation of the embedding (tools/precision_study.py) against
+    # the 1e-3 parity gate.  False = bf16x3 everywhere (~1e-5).  Training always uses bf16x3.
+    RECURRENT_FP16 = True
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
 
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
@@ -130,9 +134,9 @@ class Model(object):
             N = 8 * hdim
             w2 = K.split_operand(Wf[:I], True, rows_total=N, row0=0)
             K.split_operand(Wb[:I], True, out=w2, rows_total=N, row0=4 * hdim)
-            ent = (w2, torch.cat([Bf, Bb]))
+            ent = (w2, torch.cat([Bf, Bb]), K.lstm_pack_wh([Wf, Wb], I, hdim))
             self._packed[name] = ent
-        w2, bias2 = ent
+        w2, bias2, wh_packed = ent
         prev = self._last_split
         a2 = prev[1] if prev is not None and prev[0] is s_x else K.split_operand(s_x.reshape(B * T, I), False)
         pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=T).view(T, B, 2, 4 * hdim)
@@ -140,7 +144,8 @@ class Model(object):
             self._stagger_pending = False
             self._stagger_event = torch.cuda.current_stream().record_event()
         K.stamp('%s gemm' % name)
-        out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True)
+        out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
+                                    wh_packed=wh_packed, backend=2 if self.RECURRENT_FP16 else 1)
         K.stamp('%s lstm' % name)
         self._last_split = (out, out_split)
         return out

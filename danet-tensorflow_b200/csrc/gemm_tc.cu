@@ -5,9 +5,10 @@
 // three products hi*hi + hi*lo + lo*hi accumulate in fp32 in TMEM ("bf16x3", ~1e-5).
 //   1. split kernels write A -> [hi;lo] bf16 [2M, Kp] and W^T -> [hi;lo] bf16 [2N, Kp]
 //      (K-major, K zero-padded to a multiple of 64) into the caller's workspace;
-//   2. gemm kernel: 128x128 output tile per CTA, TMA (SWIZZLE_128B) -> 3-stage smem ring ->
-//      tcgen05.mma kind::f16 M128 N128 K16, accumulator in 128 TMEM columns, epilogue warps
-//      tcgen05.ld -> + bias -> global (optionally [B,T] -> [T,B] row remap).
+//   2. gemm kernel: 128x128 output tiles, TMA (SWIZZLE_128B) -> 3-stage smem ring -> tcgen05.mma kind::f16
+//      M128 N128 K16 into one of TWO 128-column TMEM accumulators, epilogue warps tcgen05.ld -> + bias -> global
+//      (optionally [B,T] -> [T,B] row remap) while the next tile's MMAs run; CTAs pick up further tiles through
+//      cluster launch control (try_cancel of pending CTAs of the same grid).
 #include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -20,7 +21,7 @@ constexpr int kTM = 128, kTN = 128, kTK = 64;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kTM * kTK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers, CLC responses */;
 
 static inline int pad_k(int K) { return (K + kTK - 1) / kTK * kTK; }
 
@@ -92,6 +93,33 @@ struct GemmParams {
   int atomic;                   // 1 when gridDim.z > 1
 };
 
+// Persistent over output tiles through CLUSTER LAUNCH CONTROL: the grid still has one CTA per tile, but a CTA that
+// finishes its tile cancels a not-yet-launched CTA of the same grid (clusterlaunchcontrol.try_cancel) and takes
+// over its tile.  Barriers, the TMEM allocation and the tensor-map prefetch are paid once per SM instead of once
+// per tile, and with TWO accumulators in TMEM the epilogue of tile k (tcgen05.ld -> global) overlaps the MMAs of
+// tile k+1.  Unlike a fixed `tile += gridDim.x` loop this needs no assumption about how many CTAs are resident:
+// the recurrent clusters of other stream groups hold whole SMs for ~0.5 ms, and tiles simply go to whichever CTAs run.
+constexpr int kClcSlots = 4;
+
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_addr, uint32_t mbar_addr) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+               ::"r"(resp_addr), "r"(mbar_addr) : "memory");
+}
+// decode a response: true + the cancelled CTA's blockIdx when a pending CTA was taken over
+__device__ __forceinline__ bool clc_query(uint32_t resp_addr, int& x, int& y, int& z) {
+  uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "+r"(x), "+r"(y), "+r"(z), "=r"(ok)
+      : "r"(resp_addr)
+      : "memory");
+  return ok != 0;
+}
+
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const GemmParams p) {
@@ -99,13 +127,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint64_t* clc_full_bar = tmem_empty_bar + 2;          // [kClcSlots]
+  uint64_t* clc_empty_bar = clc_full_bar + kClcSlots;   // [kClcSlots]
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(clc_empty_bar + kClcSlots);     // [kClcSlots] x 16 B (16-byte aligned)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_resp + 16 * kClcSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int nkb = min(p.kb_per_split, p.n_kblocks - kb0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -116,109 +145,164 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + s, 1);
+      mbar_init(tmem_empty_bar + s, 4);          // one arrival per epilogue warp
+    }
+    for (int s = 0; s < kClcSlots; ++s) {
+      mbar_init(clc_full_bar + s, 1);
+      mbar_init(clc_empty_bar + s, 5);           // MMA thread + 4 epilogue warps have read the response
+    }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTN);
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * kTN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+
+  // every role walks the same tile sequence: tile 0 = this CTA's own block index, tile k+1 = response k
+  int tx = blockIdx.x, ty = blockIdx.y, tz = blockIdx.z;
 
   if (warp == 0) {
-    if (elect_one_sync()) {   // ===== TMA producer =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        uint8_t* st = smem + s * kStageBytes;
-        mbar_arrive_expect_tx(full_bar + s, kStageBytes);
-        const int kc = (kb0 + kb) * kTK;
-        tma_load_2d(st, &map_a, full_bar + s, kc, m0);                          // A hi
-        tma_load_2d(st + kTileBytes, &map_a, full_bar + s, kc, p.M + m0);       // A lo
-        tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + s, kc, n0);         // W^T hi
-        tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + s, kc, p.N + n0);   // W^T lo
+    if (elect_one_sync()) {   // ===== TMA producer + tile scheduler =====
+      uint32_t kbc = 0;       // K blocks issued so far (ring position)
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+        // ask for the next tile now, so the answer is here when this tile's loads have been issued
+        mbar_wait(clc_empty_bar + slot, cph ^ 1);
+        mbar_arrive_expect_tx(clc_full_bar + slot, 16);
+        clc_try_cancel(smem_u32(clc_resp + 16 * slot), smem_u32(clc_full_bar + slot));
+        const int m0 = ty * kTM, n0 = tx * kTN, kb0 = tz * p.kb_per_split;
+        const int nkb = min(p.kb_per_split, p.n_kblocks - kb0);
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int s = kbc % kStages;
+          const uint32_t ph = (kbc / kStages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_arrive_expect_tx(full_bar + s, kStageBytes);
+          const int kc = (kb0 + kb) * kTK;
+          tma_load_2d(st, &map_a, full_bar + s, kc, m0);                          // A hi
+          tma_load_2d(st + kTileBytes, &map_a, full_bar + s, kc, p.M + m0);       // A lo
+          tma_load_2d(st + 2 * kTileBytes, &map_b, full_bar + s, kc, n0);         // W^T hi
+          tma_load_2d(st + 3 * kTileBytes, &map_b, full_bar + s, kc, p.N + n0);   // W^T lo
+        }
+        mbar_wait(clc_full_bar + slot, cph);
+        const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+        fence_proxy_async_smem();
+        if (!more) break;
       }
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {   // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_bf16(kTM, kTN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(full_bar + s, ph);
+      uint32_t kbc = 0;
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        const uint32_t tmem_acc = tmem_base + acc * kTN;
+        const int kb0 = tz * p.kb_per_split;
+        const int nkb = min(p.kb_per_split, p.n_kblocks - kb0);
+        mbar_wait(tmem_empty_bar + acc, aph ^ 1);        // the epilogue drained this accumulator (tile it-2)
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * kStageBytes);
-        const uint64_t a_hi = umma_desc_k_sw128(base), a_lo = umma_desc_k_sw128(base + kTileBytes);
-        const uint64_t b_hi = umma_desc_k_sw128(base + 2 * kTileBytes), b_lo = umma_desc_k_sw128(base + 3 * kTileBytes);
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int s = kbc % kStages;
+          const uint32_t ph = (kbc / kStages) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * kStageBytes);
+          const uint64_t a_hi = umma_desc_k_sw128(base), a_lo = umma_desc_k_sw128(base + kTileBytes);
+          const uint64_t b_hi = umma_desc_k_sw128(base + 2 * kTileBytes), b_lo = umma_desc_k_sw128(base + 3 * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kTK / 16; ++k) {
-          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K16 step inside the swizzle row
-          umma_bf16(tmem_acc, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
-          umma_bf16(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
-          umma_bf16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1);
+          for (int k = 0; k < kTK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K16 step inside the swizzle row
+            umma_bf16(tmem_acc, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_bf16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(empty_bar + s);                    // smem slot reusable once these MMAs retire
         }
-        umma_commit(empty_bar + s);                    // smem slot reusable once these MMAs retire
-        if (kb == nkb - 1) umma_commit(tmem_full_bar); // accumulator complete
+        umma_commit(tmem_full_bar + acc);                // accumulator complete
+        const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+        mbar_wait(clc_full_bar + slot, cph);
+        const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+        fence_proxy_async_smem();
+        mbar_arrive(clc_empty_bar + slot);
+        if (!more) break;
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: warp q owns TMEM lanes 32q..32q+31 = output rows m0+32q+lane =====
     const int q = warp - 4;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = m0 + 32 * q + lane;
-    const bool row_ok = row < p.M;
-    const size_t orow = p.T > 0 ? (size_t)(row % p.T) * p.nb + row / p.T : (size_t)row;
-    float* crow = p.C + orow * p.ldc;
     const bool vec = (p.ldc & 3) == 0;
-    const float mu = (p.row_mu && row_ok) ? __ldg(p.row_mu + row / p.rows_per_mu) : 0.f;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      const uint32_t tmem_acc = tmem_base + acc * kTN;
+      const int m0 = ty * kTM, n0 = tx * kTN;
+      mbar_wait(tmem_full_bar + acc, aph);
+      tc_fence_after();
+      const int row = m0 + 32 * q + lane;
+      const bool row_ok = row < p.M;
+      const size_t orow = p.T > 0 ? (size_t)(row % p.T) * p.nb + row / p.T : (size_t)row;
+      float* crow = p.C + orow * p.ldc;
+      const float mu = (p.row_mu && row_ok) ? __ldg(p.row_mu + row / p.rows_per_mu) : 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kTN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;                       // warp-uniform
-      float v[32];
-      tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v);
-      if (row_ok && p.atomic) {
-        // split-K: every K slice adds its partial tile (C was zeroed, or holds the value to accumulate onto)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) atomicAdd(crow + n, v[j] + ((p.bias && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f));
-        }
-      } else if (row_ok) {
-        if (vec && n0 + c0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.row_mu) {
-              const float4 ss = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + j));
-              o.x = fmaf(-mu, ss.x, o.x); o.y = fmaf(-mu, ss.y, o.y); o.z = fmaf(-mu, ss.z, o.z); o.w = fmaf(-mu, ss.w, o.w);
-            }
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (p.accumulate) {
-              const float4 cc = *reinterpret_cast<const float4*>(crow + n0 + c0 + j);
-              o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
-            }
-            *reinterpret_cast<float4*>(crow + n0 + c0 + j) = o;
-          }
-        } else {
+      for (int c0 = 0; c0 < kTN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;                       // warp-uniform
+        float v[32];
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v);
+        if (row_ok && p.atomic) {
+          // split-K: every K slice adds its partial tile (C was zeroed, or holds the value to accumulate onto)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
-            if (n < p.N)
-              crow[n] = v[j] - (p.row_mu ? mu * __ldg(p.col_s + n) : 0.f) + (p.bias ? __ldg(p.bias + n) : 0.f) +
-                        (p.accumulate ? crow[n] : 0.f);
+            if (n < p.N) atomicAdd(crow + n, v[j] + ((p.bias && tz == 0) ? __ldg(p.bias + n) : 0.f));
+          }
+        } else if (row_ok) {
+          if (vec && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.row_mu) {
+                const float4 ss = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + j));
+                o.x = fmaf(-mu, ss.x, o.x); o.y = fmaf(-mu, ss.y, o.y); o.z = fmaf(-mu, ss.z, o.z); o.w = fmaf(-mu, ss.w, o.w);
+              }
+              if (p.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              if (p.accumulate) {
+                const float4 cc = *reinterpret_cast<const float4*>(crow + n0 + c0 + j);
+                o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+              }
+              *reinterpret_cast<float4*>(crow + n0 + c0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N)
+                crow[n] = v[j] - (p.row_mu ? mu * __ldg(p.col_s + n) : 0.f) + (p.bias ? __ldg(p.bias + n) : 0.f) +
+                          (p.accumulate ? crow[n] : 0.f);
+            }
           }
         }
       }
+      // accumulator drained (tcgen05.wait::ld ran inside every tmem_ld): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+      const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+      mbar_wait(clc_full_bar + slot, cph);
+      const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(clc_empty_bar + slot);
+      if (!more) break;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_acc, kTN);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * kTN);
 }
 
 // ---- host -------------------------------------------------------------------------------

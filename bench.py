@@ -68,17 +68,18 @@ def reference_params(seed=1337):
 
 
 def cpu_reference_rate(wav, threads, repeats=1):
-    """mixtures/sec of the CPU restatement (oracle) on `wav` [b, N]"""
+    """mixtures/sec of the CPU restatement (oracle) on `wav` [b, N], and its separated waveforms"""
     from oracle import danet_oracle as O
     torch.set_num_threads(threads)
     P = reference_params()
     O.separate_waveforms(wav[:1, :2048], P, dtype=torch.float32)      # warm the thread pool
     best = float('inf')
+    out = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        O.separate_waveforms(wav, P, dtype=torch.float32)
+        out = O.separate_waveforms(wav, P, dtype=torch.float32)[0]
         best = min(best, time.perf_counter() - t0)
-    return wav.shape[0] / best, best
+    return wav.shape[0] / best, best, np.asarray(out)
 
 
 class ClockSampler(threading.Thread):
@@ -158,12 +159,15 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, where):
+def workload_config(batch, where, recurrent_fp16=False):
     return {'workload': 'cfg2-infer: wav->STFT->logmag->BiLSTM 4x(300+300)->anchor(6)->softmax mask x mix->iSTFT',
             'batch_per_gpu': batch, 'n_speakers': N_SPK, 'samples': N_SAMPLES, 'frames': 501, 'fft': 256,
             'hop': 64, 'embed': EMBED, 'estimator': 'anchor', 'separator': 'dot-softmax-orig',
             'parallelism': 'utterance-sharded, no collective', 'l2': 'flushed between timed steps', 'where': where,
-            'schedule': 'CUDA graph, 4 stream groups of 8 utterances, staggered'}
+            'schedule': 'CUDA graph, 4 stream groups of 8 utterances, staggered',
+            'arithmetic': 'fp32 in / out; tensor-core products on bf16 hi/lo splits (3 products, fp32 accumulate)' +
+                          ('; the recurrent product takes h_{t-1} as one fp16 value x fp16 hi/lo weights'
+                           if recurrent_fp16 else '')}
 
 
 def main():
@@ -180,6 +184,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1 = replay the step from a CUDA graph (default), 0 = eager')
     ap.add_argument('--train-steps', type=int, default=3, help='timed training steps for the extra "train" key (0 = skip)')
+    ap.add_argument('--recurrent-fp16', type=int, default=1,
+                    help='1 (default) = inference carries h into the recurrent product as fp16 (C-ABI backend 2, ~1e-4 of the '
+                         'embedding scale); 0 = bf16 hi/lo everywhere (~1e-5)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -200,6 +207,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     if args.backend is not None:
         K.DEFAULT_BACKEND = args.backend
+    D.Model.RECURRENT_FP16 = bool(args.recurrent_fp16)
     D.build.build()
     D._lib.check(D._lib.load().danet_check_device(), 'check_device')
 
@@ -295,7 +303,7 @@ def main():
         train = {'value': B * world * args.train_steps / (ms_train / 1e3), 'unit': 'mixtures/s',
                  'ms_per_step': ms_train / args.train_steps, 'steps': args.train_steps,
                  'gpu_launches': K.launches,
-                 'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (fp32 BPTT kernel + tcgen05 dW/dX products), '
+                 'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (tcgen05 cluster BPTT + tcgen05 dW/dX products), '
                          'one NCCL all-reduce of the flat gradient buffer (N > 1), fused clip + Adam'}
 
     total = B * world
@@ -326,8 +334,9 @@ def main():
                 'share_of_step': (sum(lstm_ms) / ms_eager) if lstm_ms else None,
                 'timed_in': 'eager single-stream pass of the same %d steps (%.3f ms/step); the headline value '
                             'replays the step from a CUDA graph with 4 staggered stream groups' % (args.steps, ms_eager / args.steps),
-                'note': 'algorithmic fp32 flops 2*n_dir*B*H*4H*T; the kernel is bound by the latency of T '
-                        'dependent steps, not by tensor throughput'}
+                'note': 'algorithmic fp32 flops 2*n_dir*B*H*4H*T; the kernel is bound by the latency of T dependent steps '
+                        '(per step: ~540 cycles of MMAs streaming Wh out of tensor memory, ~550 of epilogue, ~620 of DSMEM '
+                        'exchange of h; profiles/r01_lstm_phase_cycles_v4_gen2.txt), not by tensor throughput'}
 
     # the other kernels of the step against their own rooflines (algorithmic bytes / flops from DESIGN.md section 6)
     hbm = peaks.get('hbm_gbs', 6650.)
@@ -360,25 +369,33 @@ def main():
                             'frac_issued': 3 * ach / peak_tf,
                             'note': note + '; "issued" counts the 3 bf16 products behind every fp32-grade product'})
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         nb = args.cpu_baseline_mixtures
-        rate, secs = cpu_reference_rate(wav_np[:nb], threads, repeats=3)
+        rate, secs, ref_out = cpu_reference_rate(wav_np[:nb], threads, repeats=3)
         cpu_baseline = {'value': rate, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
                         'sample': '%d of the %d mixtures of one step, best of 3 (%.1f s each); torch-CPU fp32 restatement of '
                                   'the TF1 graph' % (nb, B, secs)}
+        # the checker at work on the timed configuration: separated waveforms of the LAST timed e2e step vs the oracle
+        got = out_host[:nb].numpy()
+        parity = {'max_rel_err': float(np.abs(got - ref_out).max() / np.abs(ref_out).max()), 'tolerance': 1e-3,
+                  'what': 'separated waveforms of the e2e step vs the CPU oracle (fp32) on the same %d mixtures, '
+                          'max-norm relative' % nb}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'mixtures/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (bf16x3 split operands on tcgen05, fp32 accumulate)'
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': ('f32 (tcgen05 products on bf16 hi/lo splits, fp32 accumulate' +
+                  ('; recurrent state enters its product as fp16)' if args.recurrent_fp16 else ')'))
         if K.DEFAULT_BACKEND == 1 else 'f32',
-        'data': 'synthetic', 'config': workload_config(B, 'cuda'),
+        'data': 'synthetic', 'config': workload_config(B, 'cuda', bool(args.recurrent_fp16) and K.DEFAULT_BACKEND == 1),
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
         'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train, 'kernels': kernels,
+        'parity': parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -41,10 +41,10 @@ def rnd(x, fmt):
     raise KeyError(fmt)
 
 
-def lstm_layer(x, W, B, hfmt, wfmt):
+def lstm_layer(x, W, B, hfmt, wfmt, xfmt='exact'):
     Bsz, T, I = x.shape
     H = B.shape[0] // 4
-    pre = x @ W[:I] + B
+    pre = rnd(x, xfmt) @ W[:I] + B          # hoisted input projection: activations in `xfmt`, weights exact (hi + lo)
     Wh = rnd(W[I:], wfmt)
     c = x.new_zeros(Bsz, H); h = x.new_zeros(Bsz, H)
     out = []
@@ -58,15 +58,17 @@ def lstm_layer(x, W, B, hfmt, wfmt):
     return torch.stack(out, 1)
 
 
-def encoder(x, hfmt, wfmt):
+def encoder(x, hfmt, wfmt, xfmt='exact', pfmt='exact'):
     x = x - x.mean(dim=(1, 2), keepdim=True)
     for l in range(4):
         n = 'encoder/lstm%d_%s/LSTM/linear/'
-        hf = lstm_layer(x, P[n % (l, 'fwd') + 'W'], P[n % (l, 'fwd') + 'B'], hfmt, wfmt)
-        hb = torch.flip(lstm_layer(torch.flip(x, [1]), P[n % (l, 'bwd') + 'W'], P[n % (l, 'bwd') + 'B'], hfmt, wfmt), [1])
+        hf = lstm_layer(x, P[n % (l, 'fwd') + 'W'], P[n % (l, 'fwd') + 'B'], hfmt, wfmt, xfmt)
+        hb = torch.flip(lstm_layer(torch.flip(x, [1]), P[n % (l, 'bwd') + 'W'], P[n % (l, 'bwd') + 'B'], hfmt, wfmt, xfmt), [1])
         x = torch.cat([hf, hb], -1)
-    x = x - x.mean(dim=(1, 2), keepdim=True)
-    return (x @ P['encoder/output/W']).reshape(x.shape[0], x.shape[1], 129, 20)
+    # output projection on the UNcentred operand (the centring is a rank-1 epilogue term): activations in `pfmt`
+    mu = x.mean(dim=(1, 2), keepdim=True)
+    W = P['encoder/output/W']
+    return (rnd(x, pfmt) @ W - mu * W.sum(0)).reshape(x.shape[0], x.shape[1], 129, 20)
 
 
 def separated(V):
@@ -86,3 +88,11 @@ for hfmt, wfmt in (('bf16x2', 'bf16x2'), ('fp16', 'bf16x2'), ('fp16', 'fp16x2'),
     s = separated(V)
     es = ((s - ref_s).abs().max() / ref_s.abs().max()).item()
     print('%-34s %12.3g %12.3g' % (hfmt + ' / ' + wfmt, e, es))
+print('dense products too: activations of the hoisted input products (x) / of the output projection (p) as one fp16 value')
+for hfmt, wfmt, xfmt, pfmt in (('fp16', 'fp16x2', 'fp16', 'exact'), ('fp16', 'fp16x2', 'fp16', 'fp16'),
+                               ('fp16', 'fp16', 'fp16', 'fp16'), ('exact', 'exact', 'fp16', 'fp16')):
+    V = encoder(x0, hfmt, wfmt, xfmt, pfmt)
+    e = ((V - ref).abs().max() / ref.abs().max()).item()
+    s = separated(V)
+    es = ((s - ref_s).abs().max() / ref_s.abs().max()).item()
+    print('%-34s %12.3g %12.3g' % ('%s / %s, x %s, p %s' % (hfmt, wfmt, xfmt, pfmt), e, es))

@@ -45,17 +45,18 @@ def synth_mixtures(batch, n_samples, seed):
     return synth_sources(batch, n_samples, seed).sum(1).astype(np.float32)
 
 
-def synth_sources(batch, n_samples, seed):
+def synth_sources(batch, n_samples, seed, n_spk=None):
     """the per-source waveforms [B, C, N] behind synth_mixtures (training consumes the sources)"""
+    n_spk = n_spk or N_SPK
     rs = np.random.RandomState(seed)
-    x = rs.standard_normal((batch, N_SPK, n_samples)).astype(np.float64)
+    x = rs.standard_normal((batch, n_spk, n_samples)).astype(np.float64)
     y = np.empty_like(x)
-    acc = np.zeros((batch, N_SPK))
+    acc = np.zeros((batch, n_spk))
     for i in range(n_samples):
         acc = 0.9 * acc + x[..., i]
         y[..., i] = acc
     t = np.arange(n_samples) / 8000.
-    ph = rs.uniform(0, 2 * np.pi, (batch, N_SPK, 1))
+    ph = rs.uniform(0, 2 * np.pi, (batch, n_spk, 1))
     y *= 0.5 - 0.5 * np.cos(2 * np.pi * 4. * t + ph)
     y *= 1000. / np.sqrt((y ** 2).mean(-1, keepdims=True))
     return y.astype(np.float32)
@@ -184,6 +185,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1 = replay the step from a CUDA graph (default), 0 = eager')
     ap.add_argument('--train-steps', type=int, default=3, help='timed training steps for the extra "train" key (0 = skip)')
+    ap.add_argument('--extras', type=int, default=1,
+                    help='1 = also time BASELINE.json configs[3] (3 speakers, 8 s, E = 40, k-means) and configs[4] (one 30 s '
+                         'stream, latency) on rank 0 and report them under "other_configs"')
     ap.add_argument('--recurrent-fp16', type=int, default=1,
                     help='1 (default) = inference carries h into the recurrent product as fp16 (C-ABI backend 2, ~1e-4 of the '
                          'embedding scale); 0 = bf16 hi/lo everywhere (~1e-5)')
@@ -306,6 +310,40 @@ def main():
                  'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (tcgen05 cluster BPTT + tcgen05 dW/dX products), '
                          'one NCCL all-reduce of the flat gradient buffer (N > 1), fused clip + Adam'}
 
+    # ---- extra: the other single-GPU configurations of BASELINE.json (parity cases in tests/, timed here for the record)
+    other = None
+    if args.extras and rank == 0:
+        other = []
+        for name, b2, n2, c2, e2_, est in (('configs[3]: 3 spk, 8 s, E = 40, k-means (5 iterations)', 16, 64000, 3, 40, 'kmeans'),
+                                           ('configs[4]: one 30 s stream, anchor estimator', 1, 240000, 2, 20, 'anchor')):
+            hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD=est, INFER_ESTIMATOR_METHOD=est,
+                         SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=b2, EMBED_SIZE=e2_, MAX_N_SIGNAL=c2))
+            hp.digest()
+            m2 = D.Model('other', dev, seed=1337).build()
+            w2 = torch.from_numpy(synth_sources(b2, n2, 4242, c2).sum(1).astype(np.float32)).pin_memory()
+            o2 = torch.empty((b2, c2, 64 * K.num_frames(n2)), dtype=torch.float32).pin_memory()
+            for _ in range(3):
+                m2.separate_host(w2, o2)
+            torch.cuda.synchronize()
+            lat = []
+            for _ in range(7):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m2.separate_host(w2, o2)
+                e1.record()
+                torch.cuda.synchronize()
+                lat.append(e0.elapsed_time(e1))
+            med = float(np.median(lat))
+            other.append({'config': name, 'batch': b2, 'samples': n2, 'frames': K.num_frames(n2), 'ms_per_step_e2e': med,
+                          'mixtures_per_s_e2e': b2 / med * 1e3, 'audio_seconds_per_second': b2 * n2 / 8000. / (med * 1e-3),
+                          'what': 'pinned host waveforms in -> separated waveforms in pinned host memory, CUDA graph replay, '
+                                  'median of 7, L2 flushed'})
+            del m2
+        hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                     SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=args.batch, EMBED_SIZE=EMBED, MAX_N_SIGNAL=N_SPK))
+        hp.digest()
+
     total = B * world
     value = total * args.steps / (ms_dev / 1e3)
     e2e = total * args.steps / (ms_e2e / 1e3)
@@ -395,7 +433,7 @@ def main():
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
         'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train, 'kernels': kernels,
-        'parity': parity,
+        'parity': parity, 'other_configs': other,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -15,7 +15,7 @@
 namespace danet {
 
 int lstm_bwd_tc(const float* d_out, float* gates, const float* cell_seq, const float* const* host_Wh, long long ldw,
-                int n_dir, int T, int B, int H, cudaStream_t stream);
+                int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 constexpr int kKS = 4;      // split of the 4H reduction across lanes
 
@@ -237,7 +237,7 @@ extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float*
   DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq_bwd: backend %d", backend);
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
-  if (backend == 1) return lstm_bwd_tc(d_out, gates, cell_seq, host_Wh, ldw, n_dir, T, B, H, st);
+  if (backend == 1) return lstm_bwd_tc(d_out, gates, cell_seq, host_Wh, ldw, n_dir, T, B, H, workspace, workspace_bytes, st);
   LstmBwdParams p;
   p.d_out = d_out; p.gates = gates; p.cell_seq = cell_seq;
   p.Wh[0] = host_Wh[0];

@@ -473,6 +473,14 @@ class Model(object):
         graph.replay()
         return static_out
 
+    OVERLAP_WEIGHT_GRADS = True        # training: dW / db products on a side stream under the next layer's BPTT
+
+    def side_stream(self, key):
+        st = self._twins.get(key)
+        if st is None:
+            st = self._twins[key] = torch.cuda.Stream(device=self.device)
+        return st
+
     LSTM_PRIORITY_STREAM = True        # measured: 2.862 -> 2.838 ms per step (tools/ab_groups.py)
 
     def _priority_twin(self, stream):

@@ -152,34 +152,53 @@ class _RecurrentEncoder(Encoder):
 
     def backward(self, d_embed2, tape):
         """d_embed2 [B*T, F*E] -> fills model.grads: output projection, centring, then per layer the BPTT kernel
-        and the dWx / dWh / db / dX products on its in-place gate gradients"""
+        and the dWx / dWh / db / dX products on its in-place gate gradients.
+
+        Only  BPTT(l) -> dX(l) -> BPTT(l-1)  is a dependency chain; the weight and bias gradients of layer l are leaves.
+        They run on a side stream under the next layer's BPTT, whose clusters occupy 80 of the 148 SMs and wait on
+        DSMEM latency most of the time (measured: 13.1 -> see DESIGN.md section 7)."""
         model = self.model
         g, P = model.grads, model.params
         xc = tape[-1]['centered']
         B, T, odim = xc.shape
-        K.gemm(xc.view(B * T, odim), d_embed2, trans_a=True, out=g[self.name + '/output/W'])     # dW = X^T dY
+        main = K.torch.cuda.current_stream()
+        side = model.side_stream('grad') if model.OVERLAP_WEIGHT_GRADS else main
         dx = K.gemm(d_embed2, P[self.name + '/output/W'], trans_b=True)                          # dX = dY W^T
+        side.wait_stream(main)
+        with K.torch.cuda.stream(side):
+            K.gemm(xc.view(B * T, odim), d_embed2, trans_a=True, out=g[self.name + '/output/W'])  # dW = X^T dY
         dx = K.center(dx.view(B, T, odim))             # the gradient of x - mean(x) is the same centring
         for l in range(len(tape) - 2, -1, -1):
             rec = tape[l]
             H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
             names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if self.BIDIR else [rec['name']]
             Ws = [P[n + '/LSTM/linear/W'] for n in names]
-            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)                   # [n_dir,T,B,4H]
+            if side is not main:
+                # the clusters of the backward recurrence need whole SMs: queue them ahead of the side stream's tiles
+                hp_stream = model._priority_twin(main)
+                hp_stream.wait_stream(main)
+                with K.torch.cuda.stream(hp_stream):
+                    da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)           # [n_dir,T,B,4H]
+                main.wait_stream(hp_stream)
+            else:
+                da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)
             x2 = x.reshape(B * T, I)
             out2 = rec['out'].view(B * T, -1)
-            dx_prev = K.torch.empty((B * T, I), dtype=K.torch.float32, device=x.device) if l > 0 else None
-            for d, n in enumerate(names):
-                da_d = da[d].view(T * B, 4 * H)
-                dW = g[n + '/LSTM/linear/W']
-                K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                           # sum X[b,t]^T da[t,b]
-                K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,               # sum h[b,t-+1]^T da[t,b]
-                       shift_a=-1 if d == 0 else 1, out=dW[I:])
-                K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
-                if l > 0:
-                    K.gemm(da_d, Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
-            if l > 0:
+            if l > 0:                                                                            # critical path first
+                dx_prev = K.torch.empty((B * T, I), dtype=K.torch.float32, device=x.device)
+                for d, n in enumerate(names):
+                    K.gemm(da[d].view(T * B, 4 * H), Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
                 dx = dx_prev.view(B, T, I)
+            side.wait_stream(main)                     # da is final (and, harmlessly, dX(l) has been queued)
+            with K.torch.cuda.stream(side):
+                for d, n in enumerate(names):
+                    da_d = da[d].view(T * B, 4 * H)
+                    dW = g[n + '/LSTM/linear/W']
+                    K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                       # sum X[b,t]^T da[t,b]
+                    K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,           # sum h[b,t-+1]^T da[t,b]
+                           shift_a=-1 if d == 0 else 1, out=dW[I:])
+                    K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
+        main.wait_stream(side)
 
 
 @hparams.register_encoder('lstm-orig')

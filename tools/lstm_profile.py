@@ -52,6 +52,9 @@ def run(label, env, wh_packed, backend=1):
     if prof[0, 10]:
         print('   prologue %d cycles, loop %d, tail %d' % (prof[0, 11] - prof[0, 10], prof[0, 12] - prof[0, 11],
                                                           prof[0, 13] - prof[0, 12]))
+        ns = prof[0, 15] - prof[0, 14]
+        print('   CTA (0,0,0) lived %.1f us by %%globaltimer = %d cycles -> SM clock %.0f MHz during the kernel'
+              % (ns / 1e3, prof[0, 13] - prof[0, 10], (prof[0, 13] - prof[0, 10]) / (ns / 1e3)))
     return out
 
 

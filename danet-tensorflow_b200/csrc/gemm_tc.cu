@@ -391,8 +391,8 @@ int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float*
   {
     const int tiles = (int)(grid.x * grid.y), sms = num_sms();
     int splits = 1;
-    if (tiles * 2 <= sms && p.n_kblocks >= 16 && !row_mu) {
-      splits = sms / tiles;
+    if (tiles * 4 <= sms * 3 && p.n_kblocks >= 16 && !row_mu) {
+      splits = (sms + tiles / 2) / tiles;
       const int max_splits = p.n_kblocks / 8;
       if (splits > max_splits) splits = max_splits;
       if (splits < 1) splits = 1;
@@ -481,6 +481,20 @@ extern "C" int danet_split_operand(const float* X, long long ld, int stored_k_ma
   DANET_REQUIRE(aligned16(out_bf16), DANET_E_ALIGN, "split_operand: out must be 16-byte aligned");
   const int Kp = pad_k(K);
   GemmOperand op = {X, ld, stored_k_major_rows ? 1 : 0, 0, 0};
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16) + (size_t)row0 * Kp;
+  return split_operand(op, rows, K, Kp, out, rows_total, as_stream(stream));
+}
+
+extern "C" int danet_split_operand_paired(const float* X, long long ld, int rows, int K, int perm_T, int shift,
+                                          void* out_bf16, int row0, int rows_total, void* stream) {
+  DANET_REQUIRE(X && out_bf16, DANET_E_ARG, "split_operand_paired: null pointer");
+  DANET_REQUIRE(rows >= 1 && K >= 1 && row0 >= 0 && rows_total >= row0 + rows && ld >= rows, DANET_E_SHAPE,
+                "split_operand_paired: rows %d K %d row0 %d rows_total %d ld %lld", rows, K, row0, rows_total, ld);
+  DANET_REQUIRE(perm_T >= 1 && K % perm_T == 0 && shift >= -1 && shift <= 1, DANET_E_ARG,
+                "split_operand_paired: K %d must be a multiple of perm_T %d, shift in [-1,1]", K, perm_T);
+  DANET_REQUIRE(aligned16(out_bf16), DANET_E_ALIGN, "split_operand_paired: out must be 16-byte aligned");
+  const int Kp = pad_k(K);
+  GemmOperand op = {X, ld, 1, perm_T, shift};
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16) + (size_t)row0 * Kp;
   return split_operand(op, rows, K, Kp, out, rows_total, as_stream(stream));
 }

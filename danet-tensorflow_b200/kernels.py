@@ -298,6 +298,8 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
                                              _p(pre) if keep_gates else None, _p(out_split), kp, n_dir, T, B, H,
                                              _p(ws), ws.numel(), be, _stream()), 'lstm_seq')
     _count()
+    if want_split and keep_cell:
+        return out, cell, out_split
     if want_split:
         return out, out_split
     return (out, cell) if keep_cell else out
@@ -313,6 +315,22 @@ def split_operand(x, k_major_rows, out=None, row0=0, rows_total=None):
         out = torch.empty((2 * rows_total, kp), dtype=torch.bfloat16, device=x.device)
     _lib.check(_lib.load().danet_split_operand(_p(x), x.stride(0), int(k_major_rows), rows, Kd, _p(out), row0, rows_total,
                                                _stream()), 'split_operand')
+    _count()
+    return out
+
+
+def split_operand_paired(x, perm_T, shift=0, out=None, row0=0, rows_total=None):
+    """batch-major activation x [B*T, rows] (row stride allowed) -> rows row0.. of a bf16 [2*rows_total, Kp] hi/lo operand
+    whose reduction index is time-major (k = t*B + b), optionally shifted by one step (zero filled): the A operand of
+    the weight-gradient products dW = sum_t x_t^T da_t / h_{t-+1}^T da_t"""
+    x = _req_strided(x, 'x')
+    Kd, rows = x.shape
+    rows_total = rows if rows_total is None else rows_total
+    kp = (Kd + 63) // 64 * 64
+    if out is None:
+        out = torch.empty((2 * rows_total, kp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().danet_split_operand_paired(_p(x), x.stride(0), rows, Kd, int(perm_T), int(shift), _p(out),
+                                                      row0, rows_total, _stream()), 'split_operand_paired')
     _count()
     return out
 

@@ -187,13 +187,26 @@ class Model(object):
 
     # ---------------------------------------------------------------- training step (row a16)
     def _lyr_bilstm_train(self, name, s_x, hdim, weights):
+        """lyr_bilstm keeping what the backward needs (gates in place of the pre-activations, cell states).  The layer
+        input is split to bf16 hi/lo once for both directions -- or not at all when the previous layer's recurrent kernel
+        already emitted it -- and the weights once per step (they change every step)."""
         Wf, Bf, Wb, Bb = weights
         B, T, I = s_x.shape
         x2 = s_x.reshape(B * T, I)
         pre = torch.empty((2, T, B, 4 * hdim), dtype=torch.float32, device=s_x.device)
-        K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
-        K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))
-        out, cell = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True)
+        tc = K.DEFAULT_BACKEND == 1 and hdim <= K.TC_LSTM_MAX_H
+        if tc:
+            prev = self._last_split
+            a2 = prev[1] if prev is not None and prev[0] is s_x else K.split_operand(x2, False)
+            for d, (W, Bv) in enumerate(((Wf, Bf), (Wb, Bb))):
+                K.gemm_split(a2, K.split_operand(W[:I], True), B * T, 4 * hdim, I, bias=Bv, out_perm_T=T,
+                             out=pre[d].view(T * B, 4 * hdim))
+            out, cell, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True, want_split=True)
+            self._last_split = (out, out_split)
+        else:
+            K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
+            K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))
+            out, cell = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True)
         self._tape.append(dict(name=name, x=s_x, gates=pre, cell=cell, out=out, hdim=hdim))
         return out
 

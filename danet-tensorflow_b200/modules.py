@@ -194,9 +194,13 @@ class _RecurrentEncoder(Encoder):
                 for d, n in enumerate(names):
                     da_d = da[d].view(T * B, 4 * H)
                     dW = g[n + '/LSTM/linear/W']
-                    K.gemm(x2, da_d, trans_a=True, perm_a_T=T, out=dW[:I])                       # sum X[b,t]^T da[t,b]
-                    K.gemm(out2[:, d * H:(d + 1) * H], da_d, trans_a=True, perm_a_T=T,           # sum h[b,t-+1]^T da[t,b]
-                           shift_a=-1 if d == 0 else 1, out=dW[I:])
+                    # ONE product for the stacked [I+H, 4H] gradient: A = [x ; h shifted by one step] paired
+                    # time-major with da (sum_t X[b,t]^T da[t,b], sum_t h[b,t-+1]^T da[t,b]); each operand split once
+                    a2 = K.split_operand_paired(x2, T, 0, rows_total=I + H)
+                    K.split_operand_paired(out2[:, d * H:(d + 1) * H], T, -1 if d == 0 else 1, out=a2, row0=I,
+                                           rows_total=I + H)
+                    b2 = K.split_operand(da_d, True)
+                    K.gemm_split(a2, b2, I + H, 4 * H, T * B, out=dW)
                     K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
         main.wait_stream(side)
 

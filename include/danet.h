@@ -117,9 +117,17 @@ int danet_gemm(const float* A, long long lda, int transA, int permA_T, int shift
  *   danet_gemm_split: C[M,N] (ldc) (+)= A2 * B2^T (+ bias) on split operands A2 [2M,Kp], B2 [2N,Kp];
  *     row_mu (nullable [M / rows_per_mu]) and col_s [N] subtract row_mu[row / rows_per_mu] * col_s[n]
  *     in the epilogue (mean-centring of A, app/modules.py:244-245, folded into the projection). */
+/*   danet_split_operand_paired: the transposing split (X is [K, rows]) for the weight-gradient products of the
+ *     tf.scan LSTM (main.py:125-131): the reduction index is TIME-major (k = t*nb + b, nb = K / perm_T) while X is a
+ *     batch-major [B*T, rows] activation; index k reads source row b*perm_T + t + shift, zero outside [0, perm_T)
+ *     (shift -1 / +1 pairs h_{t-1} / h_{t+1} with the gate gradients of step t).  With row0 / rows_total the layer
+ *     input and the shifted hidden sequence land in ONE operand [x ; h], i.e. one product for the stacked
+ *     [I+H, 4H] weight gradient. */
 size_t danet_split_operand_bytes(int rows, int K);
 int danet_split_operand(const float* X, long long ld, int stored_k_major_rows, int rows, int K,
                         void* out_bf16, int row0, int rows_total, void* stream);
+int danet_split_operand_paired(const float* X, long long ld, int rows, int K, int perm_T, int shift,
+                               void* out_bf16, int row0, int rows_total, void* stream);
 int danet_gemm_split(const void* A2, const void* B2, const float* bias, const float* row_mu,
                      const float* col_s, int rows_per_mu, float* C, long long ldc,
                      int M, int N, int K, int out_perm_T, int accumulate, void* stream);

@@ -149,6 +149,29 @@ def test_linear(K, backend, M, N, K_, T):
     assert rel(out, ref) < (2e-6 if backend == 0 else 3e-5)
 
 
+def test_split_operand_paired_weight_gradient(K):
+    """danet_split_operand_paired + danet_gemm_split: dW = [x ; h shifted]^T da with the batch-major / time-major pairing
+    of the tf.scan gradient (main.py:125-131, 357-358), against float64"""
+    rs = np.random.RandomState(5)
+    B, T, I, H = 3, 7, 20, 12
+    x = rs.standard_normal((B, T, I)).astype(np.float32)
+    h = rs.standard_normal((B, T, 2 * H)).astype(np.float32)        # fwd | bwd, the layer output
+    da = rs.standard_normal((T, B, 4 * H)).astype(np.float32)       # time-major gate gradients
+    xg, hg, dag = cuda(x).view(B * T, I), cuda(h).view(B * T, 2 * H), cuda(da).view(T * B, 4 * H)
+    for d, shift in ((0, -1), (1, 1)):
+        a2 = K.split_operand_paired(xg, T, 0, rows_total=I + H)
+        K.split_operand_paired(hg[:, d * H:(d + 1) * H], T, shift, out=a2, row0=I, rows_total=I + H)
+        dW = K.gemm_split(a2, K.split_operand(dag, True), I + H, 4 * H, T * B)
+        hs = np.zeros((B, T, H))
+        if shift < 0:
+            hs[:, 1:] = h[:, :-1, :H]
+        else:
+            hs[:, :-1] = h[:, 1:, H:]
+        xh = np.concatenate([x.astype(np.float64), hs], -1)                       # [B,T,I+H]
+        ref = np.einsum('btk,tbn->kn', xh, da.astype(np.float64))
+        assert rel(dW, ref) < 3e-5
+
+
 # ---------------------------------------------------------------- recurrent kernel
 @pytest.mark.parametrize('backend', [0, 1, 2])
 @pytest.mark.parametrize('n_dir,B,T,I,H', [(2, 3, 12, 129, 300), (1, 2, 9, 129, 600), (2, 17, 30, 600, 300),

@@ -247,7 +247,7 @@ def main():
             kernel_events.setdefault(name, []).append((e0, e1))
             return r
         setattr(K, name, timed)
-    for nm in ('lstm_seq', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'gemm_split', 'split_operand', 'mean'):
+    for nm in ('lstm_seq', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'mask_cmul_istft', 'gemm_split', 'split_operand', 'mean'):
         instrument(nm)
 
     def barrier():
@@ -389,6 +389,8 @@ def main():
             ('attractor_anchor', 'hbm', B * 4. * TF * E, 'one read of the embedding (fp32 SIMT products: 336 MAC per bin)'),
             ('mask_cmul', 'hbm', B * (4. * TF * E + 8. * TF + 8. * N_SPK * TF), 'embedding + mixture in, separated spectra out'),
             ('istft', 'hbm', B * N_SPK * (8. * TF + 4. * 64 * T), 'spectra in, waveforms out'),
+            ('mask_cmul_istft', 'hbm', B * (4. * TF * E + 8. * TF + 4. * N_SPK * 64 * T),
+             'K4 fused: embedding + mixture in, separated waveforms out (masked spectra stay in shared memory)'),
             ('gemm_split', 'tensor', None, 'hoisted input projections (N = 2400) and the output projection (N = 2580), bf16x3')):
         ms = avg_ms(name)
         if ms is None:

@@ -63,6 +63,7 @@ PROTOTYPES = {
     'danet_attractor_kmeans_fwd': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
     'danet_mask_cmul_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_istft_fwd': (c_i, [c_f, c_i, c_i, c_f, c_v]),
+    'danet_mask_cmul_istft_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_pit_workspace_bytes': (c_sz, [c_i, c_i]),
     'danet_pit_mse_fwd': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_v, c_f, c_f, c_v, c_sz, c_v]),
 }

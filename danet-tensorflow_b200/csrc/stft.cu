@@ -169,6 +169,169 @@ istft_kernel(const float2* __restrict__ spec, int T, float* __restrict__ wav) {
   }
 }
 
+
+// K4 in one kernel: dot-product mask (app/modules.py:548-603) x complex mixture (main.py:281-284) -> utils.istft
+// (app/utils.py:53-75) for every source.  A block owns the same 29 hops + 3 halo frames of ONE mixture as
+// istft_kernel; it first evaluates mask_c(t,f) * mix(t,f) for its 32 frames and all C sources into shared memory (one
+// read of the embedding tile, the same arithmetic as mask_cmul_kernel), then runs the inverse transform and the
+// overlap-add once per source from there.  The separated spectra (8*C*T*F bytes per mixture) never exist in HBM.
+constexpr int kFusedMaxC = 4;
+constexpr int kFusedMaxE = 64;
+constexpr int kFusedThreads = 512;     // phase 1: 512 threads of loads in flight; phase 2: two sources transformed at once
+
+__global__ void __launch_bounds__(kFusedThreads)
+mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ attractors, const float2* __restrict__ mix,
+                  int C, int T, int E, int kind, float* __restrict__ wav) {
+  extern __shared__ __align__(16) uint8_t fused_smem[];
+  float2* s_buf = reinterpret_cast<float2*>(fused_smem);                    // [2 halves][16][kFftPad]
+  float2* s_tw = s_buf + 2 * 16 * kFftPad;                                  // [256]
+  float* s_win = reinterpret_cast<float*>(s_tw + kFft);                     // [256]
+  float* s_att = s_win + kFft;                                              // [C][E]
+  float2* s_spec = reinterpret_cast<float2*>(s_att + kFusedMaxC * kFusedMaxE);   // [C][32][kBins]
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int h0 = blockIdx.x * kHopsPerBlock;
+  const int f0 = h0 - 3;
+  const int last_frame = T - 5;            // range(0, 64*T - 256, 64) -> n = 0 .. T-5
+  if (tid < kFft) {
+    float sn, cs;
+    sincospif(-(float)tid * (2.f / 256.f), &sn, &cs);
+    s_tw[tid] = make_float2(cs, sn);
+    s_win[tid] = window_at(tid);
+  }
+  for (int i = tid; i < C * E; i += kFusedThreads) s_att[i] = attractors[(size_t)b * C * E + i];
+  __syncthreads();
+
+  // ---- phase 1: masked spectra of frames f0 .. f0+31 for every source -> shared memory
+  const long long TF = (long long)T * kBins;
+  const float* Vb = embed + (size_t)b * TF * E;
+  const float2* Mb = mix + (size_t)b * TF;
+#pragma unroll 2
+  for (int idx = tid; idx < kFramesPerBlock * kBins; idx += kFusedThreads) {
+    const int slot = idx / kBins, k = idx - slot * kBins;
+    const int fr = f0 + slot;
+    float m[kFusedMaxC];
+    float2 z = make_float2(0.f, 0.f);
+    if (fr >= 0 && fr <= last_frame) {
+      const long long i = (long long)fr * kBins + k;
+      float logit[kFusedMaxC];
+#pragma unroll
+      for (int c = 0; c < kFusedMaxC; ++c) logit[c] = 0.f;
+      const float4* v4 = reinterpret_cast<const float4*>(Vb + (size_t)i * E);
+      z = __ldg(Mb + i);
+      for (int e4 = 0; e4 < E / 4; ++e4) {
+        const float4 x = __ldg(v4 + e4);
+#pragma unroll
+        for (int c = 0; c < kFusedMaxC; ++c)
+          if (c < C) {
+            const float* a = s_att + c * E + 4 * e4;
+            logit[c] = fmaf(x.x, a[0], logit[c]);
+            logit[c] = fmaf(x.y, a[1], logit[c]);
+            logit[c] = fmaf(x.z, a[2], logit[c]);
+            logit[c] = fmaf(x.w, a[3], logit[c]);
+          }
+      }
+      if (kind == 0) {
+        float mx = logit[0];
+#pragma unroll
+        for (int c = 1; c < kFusedMaxC; ++c)
+          if (c < C) mx = fmaxf(mx, logit[c]);
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxC; ++c)
+          if (c < C) {
+            m[c] = expf(logit[c] - mx);
+            den += m[c];
+          }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxC; ++c)
+          if (c < C) m[c] *= inv;
+      } else {
+#pragma unroll
+        for (int c = 0; c < kFusedMaxC; ++c)
+          if (c < C) m[c] = sigmoidf_(logit[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < kFusedMaxC; ++c) m[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < kFusedMaxC; ++c)
+      if (c < C) s_spec[((size_t)c * kFramesPerBlock + slot) * kBins + k] = make_float2(z.x * m[c], z.y * m[c]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: the inverse transform and overlap-add of istft_kernel from shared memory, two sources at a time
+  // (threads 0-255 take source c0, threads 256-511 source c0 + 1)
+  const int half = tid >> 8, t8 = tid & 255;
+  const int g = t8 >> 4, j = t8 & 15;
+  const unsigned gmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+  const int fA = f0 + 2 * g, fB = fA + 1;
+  const bool okA = fA >= 0 && fA <= last_frame;
+  const bool okB = fB >= 0 && fB <= last_frame;
+  float2* my_buf = s_buf + (size_t)half * 16 * kFftPad;
+  float* fr = reinterpret_cast<float*>(my_buf + (size_t)g * kFftPad);   // [2][256] floats after the transform
+  for (int c0 = 0; c0 < C; c0 += 2) {
+    const int c = c0 + half;
+    const bool live = c < C;
+    if (live && (okA || okB)) {
+      const float2* XA = s_spec + ((size_t)c * kFramesPerBlock + 2 * g) * kBins;
+      const float2* XB = XA + kBins;
+      float2 v[16];
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int k = 16 * m + j;
+        const int kk = k <= 128 ? k : 256 - k;
+        float2 a = XA[kk];                                  // out-of-range frames were stored as zeros
+        float2 bq = XB[kk];
+        if (kk == 0 || kk == 128) { a.y = 0.f; bq.y = 0.f; }   // irfft ignores these
+        v[m] = k <= 128 ? make_float2(a.x - bq.y, a.y + bq.x) : make_float2(a.x + bq.y, -a.y + bq.x);
+      }
+      fft256_group<true>(v, j, s_tw, my_buf + (size_t)g * kFftPad, gmask);
+      __syncwarp(gmask);
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const int n = j + 16 * k2;
+        const float w = s_win[n] * (1.f / 256.f);
+        fr[n] = v[k2].x * w;
+        fr[256 + n] = v[k2].y * w;
+      }
+    } else if (live) {
+      for (int n = j; n < 512; n += 16) fr[n] = 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      float* out = wav + ((size_t)b * C + c) * kHop * T;
+      const float* frames = reinterpret_cast<const float*>(my_buf);
+      for (int idx = t8; idx < kHopsPerBlock * kHop; idx += 256) {
+        const int h = h0 + idx / kHop, r = idx % kHop;
+        if (h >= T) break;
+        float acc = 0.f, ws = 0.f;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {         // ascending frame order n = h-3 .. h, as the reference loop
+          const int n = h - d;
+          if (n >= 0 && n <= last_frame) {
+            const int slot = n - f0;
+            const int grp = slot >> 1, hf = slot & 1;
+            const float wv = s_win[r + kHop * d];
+            acc += frames[(size_t)grp * (2 * kFftPad) + hf * 256 + r + kHop * d];
+            ws += wv * wv;
+          }
+        }
+        out[(size_t)kHop * h + r] = ws != 0.f ? acc / ws : acc;
+      }
+    }
+    __syncthreads();                         // s_buf is reused by the next pair of sources
+  }
+}
+
+static size_t mask_istft_smem_bytes(int C) {
+  return (size_t)2 * 16 * kFftPad * 8 + kFft * 8 + kFft * 4 + (size_t)kFusedMaxC * kFusedMaxE * 4 +
+         (size_t)C * kFramesPerBlock * kBins * 8;
+}
+
 }  // namespace danet
 
 using namespace danet;
@@ -207,6 +370,25 @@ extern "C" int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* w
   dim3 grid((T + kHopsPerBlock - 1) / kHopsPerBlock, n_sig);
   istft_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float2*>(spec_c64), T, wav);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_mask_cmul_istft_fwd(const float* embed, const float* attractors, const float* mix_c64, float* wav,
+                                         int B, int C, int T, int E, int kind, void* stream) {
+  DANET_REQUIRE(B >= 0 && T >= 1 && C >= 1 && C <= kFusedMaxC && E >= 4 && E % 4 == 0 && E <= kFusedMaxE, DANET_E_SHAPE,
+                "mask_cmul_istft: B %d C %d (<=%d) T %d E %d (multiple of 4, <=%d)", B, C, kFusedMaxC, T, E, kFusedMaxE);
+  DANET_REQUIRE(kind == 0 || kind == 1, DANET_E_ARG, "mask_cmul_istft: kind %d", kind);
+  if (B == 0) return DANET_OK;
+  DANET_REQUIRE(embed && attractors && mix_c64 && wav, DANET_E_ARG, "mask_cmul_istft: null pointer");
+  DANET_REQUIRE(aligned16(embed) && aligned8(mix_c64), DANET_E_ALIGN,
+                "mask_cmul_istft: embed must be 16-byte, mix 8-byte aligned");
+  DANET_REQUIRE(B <= 65535, DANET_E_SHAPE, "mask_cmul_istft: B %d > 65535", B);
+  const size_t smem = mask_istft_smem_bytes(C);
+  DANET_CUDA(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((T + kHopsPerBlock - 1) / kHopsPerBlock, B);
+  mask_istft_kernel<<<grid, kFusedThreads, smem, as_stream(stream)>>>(embed, attractors, reinterpret_cast<const float2*>(mix_c64), C, T,
+                                                             E, kind, wav);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }

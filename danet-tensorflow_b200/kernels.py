@@ -466,6 +466,35 @@ def mask_cmul(embed, attractors, mix, kind, want=('sep_pwr', 'sep', 'masks'), mi
     return out
 
 
+def mask_cmul_istft(embed, attractors, mix, kind, out=None):
+    """
+    K4 in one launch [app/modules.py:548-603; main.py:281-284; app/utils.py:53-75]: embed [B,TF,E], attractors [B,C,E],
+    mix c64 [B,T,129] -> separated waveforms f32 [B,C,64*T]; the separated spectra are never written to HBM.
+    Equals istft(mask_cmul(...)['sep']).
+    """
+    embed, B, TF, E = _embed_flat(embed)
+    attractors = _req(attractors, 'attractors', dim=3)
+    mix = _req(mix, 'mix', torch.complex64, 3)
+    Cn = attractors.shape[1]
+    T = mix.shape[1]
+    if attractors.shape[0] != B or attractors.shape[2] != E:
+        raise ValueError('mask_cmul_istft: attractors %s do not match embed' % (tuple(attractors.shape),))
+    if mix.shape[0] != B or mix.shape[2] != FEATURE or T * FEATURE != TF:
+        raise ValueError('mask_cmul_istft: mix %s does not match embed' % (tuple(mix.shape),))
+    if out is None:
+        out = torch.empty((B, Cn, FFT_STRIDE * T), dtype=torch.float32, device=embed.device)
+    elif tuple(out.shape) != (B, Cn, FFT_STRIDE * T) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError('mask_cmul_istft: out must be a contiguous float32 %s' % ((B, Cn, FFT_STRIDE * T),))
+    k = SEPARATOR_KINDS[kind] if isinstance(kind, str) else int(kind)
+    _lib.check(_lib.load().danet_mask_cmul_istft_fwd(_p(embed), _p(attractors), _p(mix), _p(out), B, Cn, T, E, k,
+                                                     _stream()), 'mask_cmul_istft')
+    _count()
+    return out
+
+
+FUSED_K4_MAX_C, FUSED_K4_MAX_E = 4, 64
+
+
 def pit_mse(x, y):
     """
     [app/ops.py:374-431, 191-222; main.py:293-309]  x, y [B,C,T,F] both complex64 or both float32

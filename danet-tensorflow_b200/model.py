@@ -385,8 +385,11 @@ class Model(object):
         c = K.pit_mse(src, z)['cross']          # cross[b,i,j] = mean |s_i|^2
         return c[:, :, 0].mean(1)
 
-    def infer(self, mix, logmag=None):
-        """infer fetches (main.py:384-385): complex mixture [B,T,F] -> separated spectra [B,C,T,F]"""
+    USE_FUSED_K4 = True        # separate(): mask x mixture -> iSTFT as one kernel (the separated spectra stay on chip)
+
+    def infer(self, mix, logmag=None, want='sep', wav_out=None):
+        """infer fetches (main.py:384-385): complex mixture [B,T,F] -> separated spectra [B,C,T,F]
+        (want='wav': separated waveforms [B,C,64*T] through the fused back end)"""
         B, T, F = mix.shape
         if logmag is None:
             feats = K.mix_features(mix.view(B, 1, T, F), want=('mix_pwr', 'logmag'))
@@ -398,8 +401,10 @@ class Model(object):
         embed_flat = embed.view(B, T * F, -1)
         attrs = self.infer_estimator(embed, s_embed_flat=embed_flat)
         K.stamp('attractor')
-        out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=('sep',))
-        return out['sep']
+        if want == 'wav':
+            return self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=('wav',), s_wav_out=wav_out)['wav']
+        out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=(want,))
+        return out[want]
 
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
     PIPELINE_MAX_GROUPS = 4
@@ -427,12 +432,20 @@ class Model(object):
                 w = w.to(self.device, non_blocking=True)
             mix, logmag = K.stft(w, want_logmag=True)
             K.stamp('g%d stft' % lo)
-            sep = self.infer(mix, logmag=logmag)
-            K.stamp('g%d mask' % lo)
-            if out.is_cuda:
-                K.istft(sep, out=out[lo:hi])
+            fused = (self.USE_FUSED_K4 and getattr(self.separator, 'SUPPORTS_WAV', False) and Cn <= K.FUSED_K4_MAX_C
+                     and hparams.EMBED_SIZE <= K.FUSED_K4_MAX_E and hparams.EMBED_SIZE % 4 == 0)
+            if fused:
+                wavs = self.infer(mix, logmag=logmag, want='wav', wav_out=out[lo:hi] if out.is_cuda else None)
+                K.stamp('g%d mask' % lo)
+                if not out.is_cuda:
+                    out[lo:hi].copy_(wavs, non_blocking=True)
             else:
-                out[lo:hi].copy_(K.istft(sep), non_blocking=True)
+                sep = self.infer(mix, logmag=logmag)
+                K.stamp('g%d mask' % lo)
+                if out.is_cuda:
+                    K.istft(sep, out=out[lo:hi])
+                else:
+                    out[lo:hi].copy_(K.istft(sep), non_blocking=True)
             K.stamp('g%d end' % lo)
 
         if groups <= 1:

@@ -281,10 +281,16 @@ class KMeansEstimator(AnchoredEstimator):
 class _DotSeparator(Separator):
     KIND = None
 
-    def __call__(self, s_mixed_signals_pwr, s_attractors, s_embed_flat, s_mixed_signals=None, want=('sep_pwr',)):
+    SUPPORTS_WAV = True      # want=('wav',): the fused back end
+
+    def __call__(self, s_mixed_signals_pwr, s_attractors, s_embed_flat, s_mixed_signals=None, want=('sep_pwr',),
+                 s_wav_out=None):
         """The reference signature returns magnitudes [B,C,T,F].  Extension: passing the complex
         mixture and `want` also yields the re-phased spectra (main.py:281-284) and the masks from the
         same pass."""
+        if tuple(want) == ('wav',):
+            # demo path (main.py:660-695): straight to waveforms, mask x mixture -> iSTFT in one kernel
+            return dict(wav=K.mask_cmul_istft(s_embed_flat, s_attractors, s_mixed_signals, self.KIND, out=s_wav_out))
         out = K.mask_cmul(s_embed_flat, s_attractors, s_mixed_signals, self.KIND, want=want,
                           mix_pwr=s_mixed_signals_pwr)
         if hparams.DEBUG and out.get('masks') is not None:

@@ -239,6 +239,14 @@ int danet_mask_cmul_fwd(const float* embed, const float* attractors,
  * overlap-add of irfft(X[n])*w, division by sum(w^2) where non-zero, length 64*T.
  * spec [n_sig,T,129] complex -> wav [n_sig, 64*T] fp32. */
 int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* stream);
+/* K4 fused (north star item 4): DotSeparatorSoftmax / DotSeparatorSigmoid (app/modules.py:548-603), the re-phasing
+ * of main.py:281-284 and utils.istft (app/utils.py:53-75) for every source in ONE kernel:
+ *   wav[b,c,:] = istft( mask_c(V[b], A[b]) * mix[b] ),  mask = softmax over c (kind 0) or sigmoid (kind 1).
+ * embed [B][T*129][E], attractors [B][C][E], mix_c64 [B][T][129] complex64 -> wav [B][C][64*T] float32.
+ * Same arithmetic as danet_mask_cmul_fwd followed by danet_istft_fwd; the separated spectra stay in shared memory.
+ * C <= 4, E a multiple of 4 and <= 64. */
+int danet_mask_cmul_istft_fwd(const float* embed, const float* attractors, const float* mix_c64, float* wav,
+                              int B, int C, int T, int E, int kind, void* stream);
 /* ---- K6  backward of the separation head ---------------------------------------------
  * What TF autodiff derives (main.py:357-358) for loss = pit_mse(src, mask*mix) with
  * mask = softmax/sigmoid(V.A) and A = estimator(V).  perm_idx comes from danet_pit_mse_fwd;

@@ -149,6 +149,30 @@ def test_linear(K, backend, M, N, K_, T):
     assert rel(out, ref) < (2e-6 if backend == 0 else 3e-5)
 
 
+@pytest.mark.parametrize('kind', ['dot-softmax-orig', 'dot-sigmoid-orig'])
+@pytest.mark.parametrize('B,C,T,E', [(2, 2, 40, 20), (1, 3, 133, 40), (3, 2, 5, 4), (2, 4, 64, 8)])
+def test_mask_cmul_istft_fused(K, kind, B, C, T, E):
+    """danet_mask_cmul_istft_fwd (north star item 4: mask x mixture -> iSTFT in one kernel) against the oracle's separator +
+    re-phasing + utils.istft, and against the two-kernel path"""
+    rs = np.random.RandomState(T + C)
+    V = rs.standard_normal((B, T * 129, E)).astype(np.float32)
+    A = rs.standard_normal((B, C, E)).astype(np.float32)
+    mix = (rs.standard_normal((B, T, 129)) + 1j * rs.standard_normal((B, T, 129))).astype(np.complex64) * 100.
+    wav = K.mask_cmul_istft(cuda(V), cuda(A), cuda(mix), kind)
+    assert wav.shape == (B, C, 64 * T)
+    two = K.istft(K.mask_cmul(cuda(V), cuda(A), cuda(mix), kind, want=('sep',))['sep'])
+    assert rel(wav, two) < 1e-6
+    mt = torch.from_numpy(mix)
+    sep_pwr = O.separator(mt.abs().double(), torch.from_numpy(A).double(), torch.from_numpy(V).double(), kind)
+    ph = torch.atan2(mt.imag, mt.real).double().unsqueeze(1)
+    sig = torch.complex(torch.cos(ph) * sep_pwr, torch.sin(ph) * sep_pwr)
+    ref = np.stack([[O.istft(sig[b, c].numpy()) for c in range(C)] for b in range(B)])
+    if np.abs(ref).max() > 0:
+        assert rel(wav, ref) < 1e-4
+    else:
+        assert float(wav.abs().max()) == 0.
+
+
 def test_split_operand_paired_weight_gradient(K):
     """danet_split_operand_paired + danet_gemm_split: dW = [x ; h shifted]^T da with the batch-major / time-major pairing
     of the tf.scan gradient (main.py:125-131, 357-358), against float64"""

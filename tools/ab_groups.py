@@ -9,6 +9,7 @@ hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 wav = torch.from_numpy(bench.synth_mixtures(B, 32000, 1)).cuda()
 D.Model.LSTM_PRIORITY_STREAM = bool(int(os.environ.get('AB_LSTM_PRIO', '0')))
+D.Model.USE_FUSED_K4 = bool(int(os.environ.get('AB_FUSED', '1')))
 m = D.Model('ab', 'cuda:0').build()
 variants = [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else '1,2,3,4'.split(','))]
 for g in variants:

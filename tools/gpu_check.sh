@@ -19,7 +19,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm
 tail -2 gpurun_out/ncu_full.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 20 -c 2 -o gpurun_out/prof_gemm python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graph 0 --train-steps 0 --extras 0 > gpurun_out/ncu_full2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attractor_partial -s 2 -c 1 -o gpurun_out/prof_attr python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graph 0 --train-steps 0 --extras 0 > gpurun_out/ncu_full3.log 2>&1
-for KN in stft_kernel mask_cmul_kernel istft_kernel; do
+for KN in stft_kernel mask_istft_kernel; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$KN -s 2 -c 1 -o gpurun_out/prof_$KN python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graph 0 --train-steps 0 --extras 0 > gpurun_out/ncu_$KN.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep

@@ -27,7 +27,7 @@ def wrap(name):
         events.setdefault(key, []).append((e0, e1))
         return r
     setattr(K, name, g)
-for n in ("stft", "istft", "center", "linear", "lstm_seq", "attractor_anchor", "mask_cmul", "mix_features"):
+for n in ("stft", "istft", "center", "linear", "lstm_seq", "attractor_anchor", "mask_cmul", "mask_cmul_istft", "gemm_split", "mean", "mix_features"):
     wrap(n)
 for _ in range(3):
     model.separate(wav, groups=int(os.environ.get("GROUPS", "1")))

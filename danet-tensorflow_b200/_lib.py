@@ -63,6 +63,9 @@ PROTOTYPES = {
     'danet_attractor_kmeans_fwd': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v, c_sz, c_v]),
     'danet_mask_cmul_fwd': (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_istft_fwd': (c_i, [c_f, c_i, c_i, c_f, c_v]),
+    'danet_conv2d_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, C.c_float, c_v]),
+    'danet_maxpool2x2_fwd': (c_i, [c_f, c_f, c_ll, c_i, c_i, c_v]),
+    'danet_add_fwd': (c_i, [c_f, c_f, c_f, c_ll, c_v]),
     'danet_mask_cmul_istft_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_pit_workspace_bytes': (c_sz, [c_i, c_i]),
     'danet_pit_mse_fwd': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_v, c_f, c_f, c_v, c_sz, c_v]),

@@ -466,6 +466,48 @@ def mask_cmul(embed, attractors, mix, kind, want=('sep_pwr', 'sep', 'masks'), mi
     return out
 
 
+def conv2d(x, w_hwio, bias=None, leak=-1.):
+    """tf.layers.conv2d(channels_first, padding='same') + bias + leaky relu max(leak*v, v) (leak < 0: none)
+    [app/modules.py:289-369; app/ops.py:103-106].  x [B,Cin,H,W]; w in TensorFlow's [k,k,Cin,Cout] layout."""
+    x = _req(x, 'x', dim=4)
+    w_hwio = _req(w_hwio, 'w', dim=4)
+    B, Cin, H, W = x.shape
+    k, k2, ci, Cout = w_hwio.shape
+    if k != k2 or ci != Cin:
+        raise ValueError('conv2d: kernel %s does not match input %s' % (tuple(w_hwio.shape), tuple(x.shape)))
+    if bias is not None:
+        bias = _req(bias, 'bias', dim=1)
+    y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().danet_conv2d_fwd(_p(x), _p(w_hwio), _p(bias), _p(y), B, Cin, Cout, H, W, k, float(leak),
+                                            _stream()), 'conv2d')
+    _count()
+    return y
+
+
+def maxpool2x2(x):
+    """tf.layers.max_pooling2d((2,2),(2,2), channels_first) [app/modules.py:299-300, 312-313]: [B,C,H,W] -> [B,C,H/2,W/2]"""
+    x = _req(x, 'x', dim=4)
+    B, Cn, H, W = x.shape
+    if H < 2 or W < 2:
+        raise ValueError('maxpool2x2: input %s is smaller than the window' % (tuple(x.shape),))
+    y = torch.empty((B, Cn, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().danet_maxpool2x2_fwd(_p(x), _p(y), B * Cn, H, W, _stream()), 'maxpool2x2')
+    _count()
+    return y
+
+
+def add(a, b):
+    """a + b (the residual connection at app/modules.py:335)"""
+    a = _req(a, 'a')
+    b = _req(b, 'b')
+    if a.shape != b.shape:
+        raise ValueError('add: shapes %s and %s differ' % (tuple(a.shape), tuple(b.shape)))
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().danet_add_fwd(_p(a), _p(b), _p(out), a.numel(), _stream()), 'add')
+    _count()
+    return out
+
+
 def mask_cmul_istft(embed, attractors, mix, kind, out=None):
     """
     K4 in one launch [app/modules.py:548-603; main.py:281-284; app/utils.py:53-75]: embed [B,TF,E], attractors [B,C,E],

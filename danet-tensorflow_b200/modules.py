@@ -3,7 +3,7 @@ Encoder / Estimator / Separator plugins -- the reference's app/modules.py surfac
 (`cls(model, name)`, called like functions, registered with `@hparams.register_*`) on
 CUDA tensors, every computation a call into libdanet_sm100.so (`kernels.py`).
 
-Registered names: encoders `toy`, `lstm-orig`, `bilstm-orig`; estimators `truth`,
+Registered names: encoders `toy`, `lstm-orig`, `bilstm-orig`, `conv-bilstm-v1`; estimators `truth`,
 `truth-threshold`, `truth-weighted`, `anchor`, `kmeans` (new); separators
 `dot-sigmoid-orig`, `dot-softmax-orig`.
 """
@@ -216,6 +216,73 @@ class LstmEncoder(_RecurrentEncoder):
 @hparams.register_encoder('bilstm-orig')
 class BiLstmEncoder(_RecurrentEncoder):
     """app/modules.py:199-260: 4 x (300 + 300)"""
+
+
+def _glorot_uniform_conv(rs, shape):
+    # tf.layers.conv2d default kernel initialiser on [k, k, cin, cout]: the fans include the receptive field
+    rf = shape[0] * shape[1]
+    lim = sqrt(6. / (rf * shape[2] + rf * shape[3]))
+    return rs.uniform(-lim, lim, size=shape)
+
+
+@hparams.register_encoder('conv-bilstm-v1')
+class ConvBiLstmEncoder(Encoder):
+    """app/modules.py:263-379, the reference's experimental CNN-LSTM hybrid: two conv + max-pool stages
+    (1 -> 8 -> 16 channels, then 16 -> 32 -> 16), a 2-layer BiLSTM (2 x FFT_SIZE hidden units) over the T/4 pooled
+    frames with a residual connection, two 3x3 convs whose 64 channels are un-pooled by depth-to-space, two 5x5 convs,
+    and a bias-free dense layer FFT_SIZE -> F*E.  T must be a multiple of 4 (the reference pads, main.py:667-671).
+    Variables are created under tf.layers' names (conv2d, conv2d_1, ..., dense) in the reference's order.
+    Inference only: no backward pass is provided for this encoder."""
+    def _conv(self, idx, x, k, cout, init=None):
+        model = self.model
+        nm = '%s/conv2d%s' % (self.name, '' if idx == 0 else '_%d' % idx)
+        w = model.get_variable(nm + '/kernel', [k, k, x.shape[1], cout], init or _glorot_uniform_conv)
+        b = model.get_variable(nm + '/bias', [cout], _zeros)
+        return K.conv2d(x, w, b, leak=hparams.RELU_LEAKAGE)
+
+    def __call__(self, s_signals, s_dropout_keep=1.):
+        _check_dropout(s_dropout_keep)
+        model = self.model
+        if model._tape is not None:
+            raise NotImplementedError('conv-bilstm-v1 has no backward pass in this build (inference only)')
+        B, T, F = s_signals.shape
+        nfft, E = hparams.FFT_SIZE, hparams.EMBED_SIZE
+        if T % 4 != 0:
+            raise ValueError('conv-bilstm-v1 needs a frame count that is a multiple of 4 (got %d)' % T)
+        if F != nfft // 2 + 1:
+            raise ValueError('conv-bilstm-v1: FEATURE_SIZE %d does not match FFT_SIZE %d' % (F, nfft))
+        r = 2. / sqrt(nfft)
+        w_init = _uniform(-r, r)
+
+        def b_init(rs, shape):                                   # :280-285: [0 | input 1 | forget -1 | output 1]
+            b = np.zeros(shape)
+            b[nfft:2 * nfft], b[2 * nfft:3 * nfft], b[3 * nfft:] = 1., -1., 1.
+            return b
+
+        x = s_signals.reshape(B, 1, T, F)
+        m0 = self._conv(0, x, 5, 8)                                               # :289-293
+        m0 = K.maxpool2x2(self._conv(1, m0, 5, 16))                               # :294-300  [B,16,T/2,64]
+        m1 = self._conv(2, m0, 3, 32)
+        m1 = K.maxpool2x2(self._conv(3, m1, 3, 16))                               # :302-313  [B,16,T/4,32]
+        T4, F8 = m1.shape[2], m1.shape[3]
+        m1 = K.center(m1.view(B, 16 * T4, F8)).view(B, 16, T4, F8)                # :315
+        m2 = m1.permute(0, 2, 1, 3).reshape(B, T4, nfft * 2)                      # :318-320
+        m2 = _lyr_bilstm('%s/lstm0' % self.name, model, m2, nfft, w_init, b_init)
+        m3 = _lyr_bilstm('%s/lstm1' % self.name, model, m2, nfft, w_init, b_init)
+        m3 = m3.reshape(B, T4, 16, F8).permute(0, 2, 1, 3).contiguous()           # :331-333
+        m3 = K.add(m3, m1)                                                        # :335
+        m3 = K.center(m3.view(B, 16 * T4, F8)).view(B, 16, T4, F8)                # :336
+        m4 = self._conv(4, m3, 3, 32, _uniform(-.3, .3))
+        m4 = self._conv(5, m4, 3, 64, _uniform(-.3, .3))                          # :342-353  [B,64,T/4,32]
+        m4 = m4.view(B, 16, 2, 2, T4, F8).permute(0, 1, 4, 2, 5, 3).reshape(B, 16, 2 * T4, 2 * F8)   # :354-357
+        m5 = self._conv(6, m4, 5, 16)
+        m5 = self._conv(7, m5, 5, 8)                                              # :359-369  [B,8,T/2,64]
+        m5 = m5.permute(0, 2, 1, 3).reshape(B * T, nfft)                          # :371-373
+        W = model.get_variable('%s/dense/kernel' % self.name, [nfft, F * E], _glorot_uniform)
+        s_out = model.dense('%s/dense/kernel' % self.name, m5, W).view(B, T, F, E)                  # :375-379
+        if hparams.DEBUG:
+            self.debug_fetches.update(conv_act=m1, lstm_act=m3, mid4=m4)
+        return s_out
 
 
 class _TruthEstimator(Estimator):

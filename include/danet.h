@@ -239,6 +239,17 @@ int danet_mask_cmul_fwd(const float* embed, const float* attractors,
  * overlap-add of irfft(X[n])*w, division by sum(w^2) where non-zero, length 64*T.
  * spec [n_sig,T,129] complex -> wav [n_sig, 64*T] fp32. */
 int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* stream);
+/* ---- conv-bilstm-v1 encoder (app/modules.py:263-379): its convolutional front and back end ----
+ * danet_conv2d_fwd: tf.layers.conv2d(data_format='channels_first', padding='same', strides 1) + bias + leaky relu
+ *   max(leak * v, v) (app/ops.py:103-106; leak < 0: linear).  x [B][Cin][H][W], y [B][Cout][H][W]; the kernel is read
+ *   in TensorFlow's variable layout [k][k][Cin][Cout], k in {1, 3, 5}.
+ * danet_maxpool2x2_fwd: tf.layers.max_pooling2d((2,2),(2,2)) on n_img = B*C images [H][W] -> [H/2][W/2] ('valid').
+ * danet_add_fwd: out = a + b (the residual at app/modules.py:335). */
+int danet_conv2d_fwd(const float* x, const float* w_hwio, const float* bias, float* y, int B, int Cin, int Cout,
+                     int H, int W, int ksize, float leak, void* stream);
+int danet_maxpool2x2_fwd(const float* x, float* y, long long n_img, int H, int W, void* stream);
+int danet_add_fwd(const float* a, const float* b, float* out, long long n, void* stream);
+
 /* K4 fused (north star item 4): DotSeparatorSoftmax / DotSeparatorSigmoid (app/modules.py:548-603), the re-phasing
  * of main.py:281-284 and utils.istft (app/utils.py:53-75) for every source in ONE kernel:
  *   wav[b,c,:] = istft( mask_c(V[b], A[b]) * mix[b] ),  mask = softmax over c (kind 0) or sigmoid (kind 1).

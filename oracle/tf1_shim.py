@@ -41,12 +41,16 @@ WANT_GRADS = True
 DEFAULT_FLOAT = 'float32'
 
 
+_LAYER_COUNT = {}
+
+
 def reset(seed=1337):
     global _RNG
     FEEDS.clear()
     VARIABLES.clear()
     GRADS.clear()
     del _SCOPE[:]
+    _LAYER_COUNT.clear()
     _RNG = np.random.RandomState(seed)
 
 
@@ -614,6 +618,59 @@ class AdamOptimizer(_Optimizer):
 LAST_OPTIMIZER = [None]
 
 
+# --------------------------------------------------------------------------
+# tf.layers (used by the conv-bilstm-v1 encoder only, app/modules.py:263-379)
+# --------------------------------------------------------------------------
+
+
+def _layer_name(base):
+    """tf.layers default naming inside the current scope: conv2d, conv2d_1, conv2d_2, ..."""
+    key = '/'.join(_SCOPE + [base])
+    n = _LAYER_COUNT.get(key, 0)
+    _LAYER_COUNT[key] = n + 1
+    return base if n == 0 else '%s_%d' % (base, n)
+
+
+def _glorot_uniform_conv(shape, dt):
+    # tf glorot_uniform on a [kh, kw, cin, cout] kernel: fans include the receptive field
+    rf = int(np.prod(shape[:-2]))
+    lim = np.sqrt(6. / (rf * shape[-2] + rf * shape[-1]))
+    return _RNG.uniform(-lim, lim, size=shape).astype(dt)
+
+
+def layers_conv2d(inputs, filters, kernel_size, strides=(1, 1), padding='valid', data_format='channels_last',
+                  activation=None, use_bias=True, kernel_initializer=None, name=None, **kw):
+    assert data_format == 'channels_first' and padding == 'same', 'only what app/modules.py:263-379 uses'
+    kh, kw_ = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    assert kh % 2 == 1 and kw_ % 2 == 1
+    x = _raw(inputs)
+    cin = int(x.shape[1])
+    with variable_scope(name or _layer_name('conv2d')):
+        kernel = get_variable('kernel', [kh, kw_, cin, filters], initializer=kernel_initializer or _glorot_uniform_conv)
+        bias = get_variable('bias', [filters], initializer=constant_initializer(0.)) if use_bias else None
+    y = torch.nn.functional.conv2d(x, kernel.v.permute(3, 2, 0, 1), None if bias is None else bias.v,
+                                   padding=(kh // 2, kw_ // 2))
+    y = TT(y)
+    return activation(y) if activation is not None else y
+
+
+def layers_max_pooling2d(inputs, pool_size, strides, padding='valid', data_format='channels_last', name=None):
+    assert data_format == 'channels_first' and padding == 'valid'
+    return TT(torch.nn.functional.max_pool2d(_raw(inputs), tuple(pool_size), tuple(strides)))
+
+
+def layers_dense(inputs, units, activation=None, use_bias=True, kernel_initializer=None, name=None, **kw):
+    x = _raw(inputs)
+    with variable_scope(name or _layer_name('dense')):
+        kernel = get_variable('kernel', [int(x.shape[-1]), units], initializer=kernel_initializer)
+        bias = get_variable('bias', [units], initializer=constant_initializer(0.)) if use_bias else None
+    y = x @ kernel.v
+    if bias is not None:
+        y = y + bias.v
+    y = TT(y)
+    return activation(y) if activation is not None else y
+
+
 def install():
     """register the fake `tensorflow` (and absent optional deps) in sys.modules"""
     tf = types.ModuleType('tensorflow')
@@ -645,7 +702,7 @@ def install():
     tf.contrib = types.SimpleNamespace(layers=types.SimpleNamespace(
         l1_regularizer=lambda s: (lambda _: None),
         l2_regularizer=lambda s: (lambda _: None)))
-    tf.layers = types.SimpleNamespace()
+    tf.layers = types.SimpleNamespace(conv2d=layers_conv2d, max_pooling2d=layers_max_pooling2d, dense=layers_dense)
     sys.modules['tensorflow'] = tf
     # optional deps of dataset readers that are off the hot path
     for name in ('h5py', 'fuel', 'fuel.datasets', 'fuel.datasets.hdf5', 'fuel.schemes'):

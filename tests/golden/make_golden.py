@@ -210,7 +210,17 @@ def ops_cases():
     print('ops -> %s (%.0f KB)' % (os.path.basename(path), os.path.getsize(path) / 1024.))
 
 
+def conv_case():
+    # the experimental CNN-LSTM hybrid (app/modules.py:263-379); T must be a multiple of 4 (two 2x2 max-pools)
+    run_model_case('convbilstm_anchor_softmax', dict(
+        ENCODER_TYPE='conv-bilstm-v1', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+        SEPARATOR_TYPE='dot-softmax-orig'), B=2, C=2, T=12, seed=11)
+
+
 def main():
+    if '--only-conv' in sys.argv:
+        conv_case()
+        return
     audio_cases()
     ops_cases()
     bl = dict(ENCODER_TYPE='bilstm-orig')
@@ -230,6 +240,7 @@ def main():
     run_model_case('toy_defaults', {}, B=2, C=2, T=8, seed=3, toy_input=True)
     run_model_case('lstm_tw_anchor_sigmoid', dict(ENCODER_TYPE='lstm-orig'),
                    B=2, C=2, T=6, seed=8)
+    conv_case()
 
 
 if __name__ == '__main__':

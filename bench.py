@@ -365,7 +365,11 @@ def main():
     achieved = flops / (lstm_avg_ms * 1e-3) / 1e12 if lstm_avg_ms else None
     roofline = {'bound': 'tensor', 'kernel': 'lstm_seq (BiLSTM recurrence, one launch per layer)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved / peak_tf if achieved else None, 'traffic': None,
+                'frac': achieved / peak_tf if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 8-utterance launch (profiles/r01_ncu_v7_lstm.txt:
+                # 41.40 + 1.72 MB; the input projections stream in once, outputs stay in L2), scaled to this launch's batch
+                'traffic': 43.12e6 * B / 8.,
+                'traffic_source': 'ncu --set full, lstm_tc2_kernel<1>, 8 utterances per launch, scaled by B / 8',
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)'
                 if peaks else 'fallback',
                 'ms_per_launch': lstm_avg_ms, 'launches_per_step': N_LAYERS,

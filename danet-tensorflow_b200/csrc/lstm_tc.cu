@@ -392,6 +392,10 @@ __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uin
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// 16 lanes x 4 columns: thread t gets (lane base + t/4, column t%4) and (lane base + 8 + t/4, column t%4); no wait
+__device__ __forceinline__ void tmem_ld_16x128b(uint32_t t0, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(t0) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x4(uint32_t t0, float (&a)[4]) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -478,7 +482,9 @@ lstm_tc2_kernel(const LstmTcParams p) {
 
   // ---- one-time: this CTA's rows of Wh^T -> packed bf16 hi/lo in TMEM (lane = gate row 4*unit + gate) ----
   if (warp < 4) {
-    const int m = tid, u = m >> 2, g = m & 3, unit = unit0 + u;
+    // TMEM lane m = 32*q + 8*gate + u holds gate `gate` of unit 8*q + u (gate-major inside each 32-lane quadrant, so that
+    // tcgen05.ld.16x128b hands one thread all four gates of a (unit, utterance) pair: see the epilogue)
+    const int m = tid, u = 8 * (m >> 5) + (m & 7), g = (m >> 3) & 3, unit = unit0 + u;
     const bool unit_ok = unit < H;
     const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
     if (p.Wh_packed) {
@@ -556,7 +562,6 @@ lstm_tc2_kernel(const LstmTcParams p) {
     const int bl = 4 * hw + g;                     // utterance inside the tile (after the butterfly)
     const int b = b0 + bl, unit = unit0 + ul;
     const bool valid = b < B && unit < H;
-    const bool g1 = (g & 1) != 0, g2 = (g & 2) != 0;
     float c = 0.f;
     float pre_q[2][4];
     auto load_pre = [&](int s, float (&dst)[4]) {
@@ -589,32 +594,30 @@ lstm_tc2_kernel(const LstmTcParams p) {
         mbar_wait(acc_full, (s - 1) & 1);
         DANET_PROF(4);
         tc_fence_after();
-        float sk[4];                                       // my gate row, utterances 4*hw + k
-        if (HF) {
-          tmem_ld_32x4(tmem_acc + lane_sel + 4 * hw, sk);
-        } else {
-          float v1[4];
-          tmem_ld_2x4(tmem_acc + lane_sel + 4 * hw, tmem_acc + lane_sel + 8 + 4 * hw, sk, v1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) sk[k] += v1[k];
+        // tcgen05.ld.16x128b at lanes 32q (+16), columns 4hw..4hw+3: thread t receives (lane base + t/4, column t%4)
+        // and (lane base + 8 + t/4, column t%4), i.e. with the gate-major row order gates 0,1 (2,3) of unit t/4 for
+        // utterance 4hw + t%4 -- exactly this thread's pair, no cross-lane regrouping (layout probed on the B200:
+        // tools/probes/tmem_ld_layout.cu)
+        {
+          const uint32_t t0 = tmem_acc + lane_sel + 4 * hw;
+          uint32_t r01[2], r23[2];
+          tmem_ld_16x128b(t0, r01);
+          tmem_ld_16x128b(t0 + ((uint32_t)16 << 16), r23);
+          if (HF) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            a[0] += __uint_as_float(r01[0]); a[1] += __uint_as_float(r01[1]);
+            a[2] += __uint_as_float(r23[0]); a[3] += __uint_as_float(r23[1]);
+          } else {                                           // columns j hold hi*lo + lo*hi, columns 8 + j hold hi*hi
+            uint32_t s01[2], s23[2];
+            tmem_ld_16x128b(t0 + 8, s01);
+            tmem_ld_16x128b(t0 + 8 + ((uint32_t)16 << 16), s23);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            a[0] += __uint_as_float(r01[0]) + __uint_as_float(s01[0]); a[1] += __uint_as_float(r01[1]) + __uint_as_float(s01[1]);
+            a[2] += __uint_as_float(r23[0]) + __uint_as_float(s23[0]); a[3] += __uint_as_float(r23[1]) + __uint_as_float(s23[1]);
+          }
         }
         DANET_PROF(5);
         tc_fence_before();
-        // stage 1 (lanes g, g^2): keep my half of the utterances, get the partner's gate for it
-        const float keep0 = g2 ? sk[2] : sk[0], keep1 = g2 ? sk[3] : sk[1];
-        const float r0 = __shfl_xor_sync(0xffffffffu, g2 ? sk[0] : sk[2], 2);
-        const float r1 = __shfl_xor_sync(0xffffffffu, g2 ? sk[1] : sk[3], 2);
-        // stage 2 (lanes g, g^1): keep utterance g, get gates g^1 and g^3 for it
-        const float mine = g1 ? keep1 : keep0, mine2 = g1 ? r1 : r0;
-        const float rA = __shfl_xor_sync(0xffffffffu, g1 ? keep0 : keep1, 1);
-        const float rB = __shfl_xor_sync(0xffffffffu, g1 ? r0 : r1, 1);
-        // gate x sits in slot g ^ x (0 mine, 1 rA, 2 mine2, 3 rB): two levels of selects, no branches
-        const float lo_e = g1 ? rA : mine, lo_o = g1 ? mine : rA;      // slots {0,1} for x even / odd
-        const float hi_e = g1 ? rB : mine2, hi_o = g1 ? mine2 : rB;    // slots {2,3}
-        a[0] += g2 ? hi_e : lo_e;
-        a[1] += g2 ? hi_o : lo_o;
-        a[2] += g2 ? lo_e : hi_e;
-        a[3] += g2 ? lo_o : hi_o;
       }
       DANET_PROF(6);
       // c = sig(i)*g + sig(f)*c ; h = sig(o)*tanh(c)   (candidate WITHOUT tanh, app/ops.py:141-147)
@@ -751,13 +754,13 @@ size_t lstm_tc_workspace_bytes(int, int, int) { return 256; }
 bool lstm_tc_supported(int H) { return H % 4 == 0 && (H + kUnits - 1) / kUnits <= kMaxCta; }
 
 // ---- Wh -> the recurrent kernel's TMEM image, once per weight update ------------------------------------------
-// [image][dir][rank][128 rows m = 4*unit + gate][ncta*16 hi words | ncta*16 lo words | 4 pad words]; word j of a row
+// [image][dir][rank][128 rows m = 32*q + 8*gate + u, unit 8*q + u][ncta*16 hi words | ncta*16 lo words | 4 pad words]; word j of a row
 // holds elements k = 2j (low half) and 2j+1 of Wh[k][gate*H + 32*rank + unit] as bf16 (image 0) or fp16 (image 1).
 __global__ void lstm_pack_wh_kernel(const float* W0, const float* W1, long long ldw, int H, int ncta, uint32_t* out) {
   const int rank = blockIdx.x, dir = blockIdx.y, m = threadIdx.x;
   const bool f16 = blockIdx.z != 0;                 // image 0: bf16 pairs (backend 1), image 1: fp16 pairs (backend 2)
   out += (size_t)blockIdx.z * gridDim.y * ncta * kRows * (size_t)(ncta * 32 + 4);
-  const int unit = rank * kUnits + (m >> 2), g = m & 3;
+  const int unit = rank * kUnits + 8 * (m >> 5) + (m & 7), g = (m >> 3) & 3;   // lane m = 32q + 8*gate + u (lstm_tc2_kernel)
   const int rw = ncta * 32 + 4;
   const float* W = dir ? W1 : W0;
   uint32_t* row = out + (((size_t)dir * ncta + rank) * kRows + m) * (size_t)rw;

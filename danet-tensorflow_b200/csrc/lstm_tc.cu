@@ -389,6 +389,9 @@ __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uin
   const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -581,6 +584,8 @@ lstm_tc2_kernel(const LstmTcParams p) {
     const uint32_t stage_off = sw64_offset(bl, ul & ~1);      // the (even, odd) unit pair of utterance bl: 4 bytes
     const uint32_t stage_addr = smem_u32(sStage) + stage_off;
     const uint32_t own_addr = smem_u32(sH + (size_t)rank * kBlk) + stage_off;
+    const uint32_t stage16_addr = smem_u32(sStage) + sw64_offset(bl, ul);            // this thread's own 16-bit slot
+    const uint32_t own16_addr = smem_u32(sH + (size_t)rank * kBlk) + sw64_offset(bl, ul);
     const bool odd = (u & 1) != 0;
     constexpr float kL2e = 1.4426950408889634f;
     for (int s = 0; s < T; ++s) {
@@ -635,30 +640,39 @@ lstm_tc2_kernel(const LstmTcParams p) {
       const float th = copysignf((1.f - ec) * roc * po, c);
       const float h = valid ? og * th : 0.f;
       DANET_PROF(7);
-      // pair up with the neighbouring unit (lane ^ 4) so 16-bit values travel as 32-bit words
-      const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
-      const float he = odd ? hn : h, ho = odd ? h : hn;        // units (ul & ~1), (ul | 1)
-      uint32_t vh, vl;
-      if (!HF) split2_bf16(he, ho, vh, vl);
-      if (s < T - 1) {
-        if (!odd) {
-          const uint32_t st = stage_addr + (uint32_t)(s & 1) * kSend;
-          const uint32_t own = own_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
-          if (HF) {
-            const __half2 v16 = __floats2half2_rn(he, ho);
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(&v16);
-            st_shared_u32(st, v);
-            st_shared_u32(own, v);
-          } else {
+      uint32_t vh = 0, vl = 0;
+      float he = 0.f, ho = 0.f;
+      if (HF) {
+        // every thread stores its own fp16 value (16-bit stores, neighbours share a word): the pairing shuffle is only
+        // needed for the global stores below, behind the barrier
+        if (s < T - 1) {
+          const unsigned short hv = __half_as_ushort(__float2half_rn(h));
+          st_shared_u16(stage16_addr + (uint32_t)(s & 1) * kSend, hv);
+          st_shared_u16(own16_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk, hv);
+          fence_proxy_async_smem();
+          asm volatile("bar.arrive 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
+          DANET_PROF(8);
+        }
+        const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
+        he = odd ? hn : h; ho = odd ? h : hn;                  // units (ul & ~1), (ul | 1)
+      } else {
+        // pair up with the neighbouring unit (lane ^ 4) so 16-bit values travel as 32-bit words
+        const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
+        he = odd ? hn : h; ho = odd ? h : hn;
+        split2_bf16(he, ho, vh, vl);
+        if (s < T - 1) {
+          if (!odd) {
+            const uint32_t st = stage_addr + (uint32_t)(s & 1) * kSend;
+            const uint32_t own = own_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
             st_shared_u32(st, vl);
             st_shared_u32(st + 512, vh);
             st_shared_u32(own, vl);
             st_shared_u32(own + 512, vh);
           }
+          fence_proxy_async_smem();
+          asm volatile("bar.arrive 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
+          DANET_PROF(8);
         }
-        fence_proxy_async_smem();
-        asm volatile("bar.arrive 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
-        DANET_PROF(8);
       }
       if (valid) {
         if (odd && p.out_split) {

@@ -20,6 +20,7 @@ PROTOTYPES = {
     'danet_last_error_string': (C.c_char_p, []),
     'danet_check_device': (c_i, []),
     'danet_timestamp': (c_i, [c_v, c_v]),
+    'danet_crc32c': (C.c_uint, [c_v, c_sz, C.c_uint]),
     'danet_stft_num_frames': (c_i, [c_i]),
     'danet_stft_fwd': (c_i, [c_f, c_i, c_i, c_f, c_f, c_v]),
     'danet_mix_features_fwd': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_v]),

@@ -54,3 +54,32 @@ extern "C" int danet_timestamp(unsigned long long* slot, void* stream) {
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
+
+// host helper of the checkpoint writer / reader (tf_bundle.py): CRC32C (Castagnoli, reflected 0x82F63B78) as
+// TensorFlow's tensor bundles store it per tensor and per table block; slicing-by-8, ~1 GB/s on one core
+extern "C" unsigned int danet_crc32c(const void* data, size_t n, unsigned int crc) {
+  static unsigned int tab[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (unsigned int i = 0; i < 256; ++i) {
+      unsigned int c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tab[0][i] = c;
+    }
+    for (unsigned int i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFF];
+    ready = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  crc = ~crc;
+  while (n >= 8) {
+    const unsigned int lo = crc ^ (p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned int)p[3] << 24));
+    const unsigned int hi = p[4] | (p[5] << 8) | (p[6] << 16) | ((unsigned int)p[7] << 24);
+    crc = tab[7][lo & 0xFF] ^ tab[6][(lo >> 8) & 0xFF] ^ tab[5][(lo >> 16) & 0xFF] ^ tab[4][lo >> 24] ^
+          tab[3][hi & 0xFF] ^ tab[2][(hi >> 8) & 0xFF] ^ tab[1][(hi >> 16) & 0xFF] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = tab[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}

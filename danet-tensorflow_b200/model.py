@@ -66,9 +66,32 @@ class Model(object):
             else:
                 self.params[k] = t
 
+    TF_SCOPE = 'global/'               # main.py:229: every trainable variable of the reference lives under this scope
+
     def save_params(self, path):
-        """main.py:192-199 -- trainable variables only (no optimiser slots)"""
-        torch.save({k: v.cpu() for k, v in self.params.items()}, path)
+        """main.py:192-199 -- trainable variables only (no optimiser slots).  `*.pt`: a torch file of {name: tensor};
+        anything else: a TensorFlow checkpoint bundle `<path>.index` + `<path>.data-00000-of-00001` under the
+        reference's variable names (tf_bundle.py), the format its tf.train.Saver writes"""
+        if path.endswith('.pt'):
+            torch.save({k: v.cpu() for k, v in self.params.items()}, path)
+            return path
+        from . import tf_bundle
+        return tf_bundle.write_bundle(path, {self.TF_SCOPE + k: v.detach().cpu().numpy() for k, v in self.params.items()})
+
+    def load_params_file(self, path):
+        """main.py:201-206: restore from a torch file (`*.pt`) or a TensorFlow checkpoint prefix.  Variables the model
+        does not have (optimiser slots, step counters) are ignored; returns the names that were loaded."""
+        if path.endswith('.pt'):
+            params = torch.load(path)
+        else:
+            from . import tf_bundle
+            prefix = path[:-6] if path.endswith('.index') else path
+            n = len(self.TF_SCOPE)
+            params = {k[n:]: v for k, v in tf_bundle.read_bundle(prefix).items() if k.startswith(self.TF_SCOPE)}
+            if self.params:
+                params = {k: v for k, v in params.items() if k in self.params}
+        self.load_params(params)
+        return sorted(params)
 
     def parameter_count(self):
         return sum(int(v.numel()) for v in self.params.values())

@@ -44,6 +44,9 @@ const char* danet_last_error_string(void);
 int         danet_check_device(void);
 /* profiling aid: a 1-thread kernel on `stream` stores %globaltimer (ns) into *slot (device memory) */
 int         danet_timestamp(unsigned long long* slot, void* stream);
+/* host-side helper (no GPU work): CRC32C (Castagnoli) continued from `crc` (0 to start), the checksum TensorFlow's
+ * checkpoint bundles carry per tensor and per table block (tf.train.Saver at main.py:192-206; tf_bundle.py) */
+unsigned int danet_crc32c(const void* data, size_t n, unsigned int crc);
 
 /* ---- K1  STFT front end -------------------------------------------------
  * replaces scipy.signal.stft as called at app/utils.py:117-122,

@@ -71,7 +71,7 @@ def main(argv=None):
     model = D.Model(args.name).build()
     model.reset()
     if args.input_pfile is not None:
-        model.load_params(torch.load(args.input_pfile))
+        model.load_params_file(args.input_pfile)          # *.pt or a TensorFlow checkpoint prefix (main.py:201-206)
     print('%d parameters' % model.parameter_count())
     B, C = hparams.BATCH_SIZE, hparams.MAX_N_SIGNAL
 

@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -94,3 +95,49 @@ def test_missing_library_fails_loudly(D, monkeypatch):
     monkeypatch.setattr(D._lib, 'LIB_PATH', '/nonexistent/libdanet_sm100.so')
     with pytest.raises(RuntimeError, match='no CPU or PyTorch fallback'):
         D._lib.load()
+
+
+# ---------------------------------------------------------------- TensorFlow checkpoint bundles (tf_bundle.py)
+def test_tf_bundle_primitives_known_answers():
+    from danet_tensorflow_b200 import tf_bundle as TB
+    assert TB._crc32c_py(b'123456789') == 0xE3069283           # the CRC-32C check value (RFC 3720 appendix B.4)
+    assert TB._crc32c_py(b'\x00' * 32) == 0x8A9136AA            # RFC 3720: 32 bytes of zeros
+    assert TB._crc32c_py(b'\xff' * 32) == 0x62A8AB43            # RFC 3720: 32 bytes of ones
+    blob = bytes(range(256)) * 5
+    assert TB.crc32c(blob) == TB._crc32c_py(blob)              # the library's host helper agrees with the table walk
+    for c in (0, 1, 0xE3069283, 0xFFFFFFFF):
+        assert TB.unmask_crc(TB.mask_crc(c)) == c
+    assert TB.mask_crc(0) == 0xA282EAD8                        # leveldb/util/crc32c.h kMaskDelta
+    assert TB.put_varint(300) == b'\xac\x02' and TB.get_varint(b'\xac\x02', 0) == (300, 2)
+    assert TB.MAGIC == 0xdb4775248b80fb57                      # leveldb/table/format.h kTableMagicNumber
+    raw = b'hello hello hello hello'
+    # a hand-assembled snappy stream: literal "hello " then a copy of 17 bytes at offset 6
+    comp = TB.put_varint(len(raw)) + bytes([(6 - 1) << 2]) + b'hello ' + bytes([((17 - 1) << 2) | 2, 6, 0])
+    assert TB._snappy_uncompress(comp) == raw
+
+
+def test_tf_bundle_round_trip(tmp_path):
+    from danet_tensorflow_b200 import tf_bundle as TB
+    rs = np.random.RandomState(0)
+    t = {'global/encoder/lstm%d_fwd/LSTM/linear/W' % i: rs.standard_normal((17 + i, 8)).astype(np.float32) for i in range(150)}
+    t['global/train_estimator/anchors'] = rs.standard_normal((6, 20)).astype(np.float32)
+    t['learn_rate'] = np.float32(3e-4)
+    t['global_step'] = np.int64(7)
+    prefix = str(tmp_path / 'sub' / 'ckpt')
+    TB.write_bundle(prefix, t, entries_per_block=16)           # several data blocks + an index block with several entries
+    assert os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
+    with open(prefix + '.index', 'rb') as f:
+        assert f.read()[-8:] == (0xdb4775248b80fb57).to_bytes(8, 'little')
+    r = TB.read_bundle(prefix)
+    assert set(r) == set(t)
+    for k in t:
+        assert r[k].dtype == np.asarray(t[k]).dtype and r[k].shape == np.asarray(t[k]).shape
+        assert np.array_equal(r[k], t[k])
+    # corruption is detected: flip one byte of a tensor
+    with open(prefix + '.data-00000-of-00001', 'r+b') as f:
+        f.seek(5)
+        b = f.read(1)
+        f.seek(5)
+        f.write(bytes([b[0] ^ 0x40]))
+    with pytest.raises(IOError):
+        TB.read_bundle(prefix)

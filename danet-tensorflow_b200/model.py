@@ -444,6 +444,11 @@ class Model(object):
         B, n = wav.shape
         if groups is None:
             groups = max(1, min(self.PIPELINE_MAX_GROUPS, B // self.PIPELINE_GROUP))
+            geo = getattr(self.encoder, '_geometry', None)
+            if geo is not None and geo()[1] > K.TC_LSTM_MAX_H:
+                # H too large for the cluster kernel (lstm-orig, H = 600): the fp32 cooperative kernel needs all its CTAs
+                # resident, so more than two groups only queue behind each other (measured 45.8 ms with 4, 31.6 with 2)
+                groups = min(groups, 2)
         Cn, T = hparams.MAX_N_SIGNAL, K.num_frames(n)
         if out is None:
             out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=self.device)

@@ -21,7 +21,10 @@ constexpr int kTM = 128, kTN = 128, kTK = 64;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kTM * kTK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers, CLC responses */;
+constexpr int kEpiLd = 36;                                // floats per row of an epilogue warp's 32 x 32 transposition tile
+constexpr int kEpiTileBytes = 32 * kEpiLd * 4;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers, CLC responses */ +
+                          4 * kEpiTileBytes /* one transposition tile per epilogue warp */;
 
 static inline int pad_k(int K) { return (K + kTK - 1) / kTK * kTK; }
 
@@ -133,6 +136,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* clc_empty_bar = clc_full_bar + kClcSlots;   // [kClcSlots]
   uint8_t* clc_resp = reinterpret_cast<uint8_t*>(clc_empty_bar + kClcSlots);     // [kClcSlots] x 16 B (16-byte aligned)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_resp + 16 * kClcSlots);
+  float* epi_tiles = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512);      // [4 warps][32][kEpiLd]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -250,40 +254,55 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (n0 + c0 >= p.N) break;                       // warp-uniform
         float v[32];
         tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v);
-        if (row_ok && p.atomic) {
-          // split-K: every K slice adds its partial tile (C was zeroed, or holds the value to accumulate onto)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.N) atomicAdd(crow + n, v[j] + ((p.bias && tz == 0) ? __ldg(p.bias + n) : 0.f));
-          }
-        } else if (row_ok) {
-          if (vec && n0 + c0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.row_mu) {
-                const float4 ss = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + j));
-                o.x = fmaf(-mu, ss.x, o.x); o.y = fmaf(-mu, ss.y, o.y); o.z = fmaf(-mu, ss.z, o.z); o.w = fmaf(-mu, ss.w, o.w);
-              }
-              if (p.bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-              }
-              if (p.accumulate) {
-                const float4 cc = *reinterpret_cast<const float4*>(crow + n0 + c0 + j);
-                o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
-              }
-              *reinterpret_cast<float4*>(crow + n0 + c0 + j) = o;
-            }
-          } else {
+        if (p.atomic) {
+          if (row_ok) {
+            // split-K: every K slice adds its partial tile (C was zeroed, or holds the value to accumulate onto)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = n0 + c0 + j;
-              if (n < p.N)
-                crow[n] = v[j] - (p.row_mu ? mu * __ldg(p.col_s + n) : 0.f) + (p.bias ? __ldg(p.bias + n) : 0.f) +
-                          (p.accumulate ? crow[n] : 0.f);
+              if (n < p.N) atomicAdd(crow + n, v[j] + ((p.bias && tz == 0) ? __ldg(p.bias + n) : 0.f));
             }
+          }
+        } else if (vec && n0 + c0 + 32 <= p.N) {
+          // Coalesced stores: a lane holds 32 columns of ITS row, and writing them directly makes every store
+          // instruction touch 32 rows (32 half-used sectors).  Transposed through a 32 x 32 shared-memory tile, one
+          // instruction writes 4 rows x 128 contiguous bytes: 8x fewer memory transactions per tile.
+          float* tile = epi_tiles + (size_t)q * 32 * kEpiLd;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tile + lane * kEpiLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int cj = 4 * (lane & 7);                         // my 4 columns of the chunk
+          float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), bb = ss;
+          if (p.row_mu) ss = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + cj));
+          if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cj));
+          const unsigned long long my_ptr = reinterpret_cast<unsigned long long>(crow);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);                   // row of the warp's 32 handled by this lane now
+            const unsigned long long rp = __shfl_sync(0xffffffffu, my_ptr, r);
+            const float rmu = __shfl_sync(0xffffffffu, mu, r);
+            const int rok = __shfl_sync(0xffffffffu, (int)row_ok, r);
+            float4 o = *reinterpret_cast<const float4*>(tile + r * kEpiLd + cj);
+            o.x = fmaf(-rmu, ss.x, o.x) + bb.x; o.y = fmaf(-rmu, ss.y, o.y) + bb.y;
+            o.z = fmaf(-rmu, ss.z, o.z) + bb.z; o.w = fmaf(-rmu, ss.w, o.w) + bb.w;
+            if (rok) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(rp) + n0 + c0 + cj);
+              if (p.accumulate) {
+                const float4 cc = *dst;
+                o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+              }
+              *dst = o;
+            }
+          }
+        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.N)
+              crow[n] = v[j] - (p.row_mu ? mu * __ldg(p.col_s + n) : 0.f) + (p.bias ? __ldg(p.bias + n) : 0.f) +
+                        (p.accumulate ? crow[n] : 0.f);
           }
         }
       }

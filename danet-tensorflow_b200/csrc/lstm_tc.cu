@@ -656,23 +656,26 @@ lstm_tc2_kernel(const LstmTcParams p) {
         const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
         he = odd ? hn : h; ho = odd ? h : hn;                  // units (ul & ~1), (ul | 1)
       } else {
-        // pair up with the neighbouring unit (lane ^ 4) so 16-bit values travel as 32-bit words
-        const float hn = __shfl_xor_sync(0xffffffffu, h, 4);
-        he = odd ? hn : h; ho = odd ? h : hn;
-        split2_bf16(he, ho, vh, vl);
+        // bf16 hi / lo of my own value as two 16-bit stores each (stage + own copy): no pairing shuffle before the barrier
+        __nv_bfloat16 bh, bl16;
+        split_bf16(h, bh, bl16);
         if (s < T - 1) {
-          if (!odd) {
-            const uint32_t st = stage_addr + (uint32_t)(s & 1) * kSend;
-            const uint32_t own = own_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
-            st_shared_u32(st, vl);
-            st_shared_u32(st + 512, vh);
-            st_shared_u32(own, vl);
-            st_shared_u32(own + 512, vh);
-          }
+          const uint32_t st = stage16_addr + (uint32_t)(s & 1) * kSend;
+          const uint32_t own = own16_addr + (uint32_t)(s & 1) * (uint32_t)ncta * kBlk;
+          st_shared_u16(st, __bfloat16_as_ushort(bl16));
+          st_shared_u16(st + 512, __bfloat16_as_ushort(bh));
+          st_shared_u16(own, __bfloat16_as_ushort(bl16));
+          st_shared_u16(own + 512, __bfloat16_as_ushort(bh));
           fence_proxy_async_smem();
           asm volatile("bar.arrive 1, %0;" ::"r"(kEpi2Threads + 32 * ncta) : "memory");
           DANET_PROF(8);
         }
+        // neighbouring units (lane ^ 4) pair up for the 32-bit global stores of the next layer's operand
+        const uint32_t mine = (uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bl16) << 16);
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 4);
+        const uint32_t e = odd ? other : mine, o = odd ? mine : other;          // units (ul & ~1), (ul | 1)
+        vh = (e & 0xffffu) | (o << 16);
+        vl = (e >> 16) | (o & 0xffff0000u);
       }
       if (valid) {
         if (odd && p.out_split) {

@@ -57,19 +57,24 @@ extern "C" int danet_timestamp(unsigned long long* slot, void* stream) {
 
 // host helper of the checkpoint writer / reader (tf_bundle.py): CRC32C (Castagnoli, reflected 0x82F63B78) as
 // TensorFlow's tensor bundles store it per tensor and per table block; slicing-by-8, ~1 GB/s on one core
-extern "C" unsigned int danet_crc32c(const void* data, size_t n, unsigned int crc) {
-  static unsigned int tab[8][256];
-  static bool ready = false;
-  if (!ready) {
+namespace {
+struct Crc32cTables {
+  unsigned int t[8][256];
+  Crc32cTables() {
     for (unsigned int i = 0; i < 256; ++i) {
       unsigned int c = i;
       for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
-      tab[0][i] = c;
+      t[0][i] = c;
     }
     for (unsigned int i = 0; i < 256; ++i)
-      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFF];
-    ready = true;
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
   }
+};
+}  // namespace
+
+extern "C" unsigned int danet_crc32c(const void* data, size_t n, unsigned int crc) {
+  static const Crc32cTables tables;                    // function-local static: initialised once, thread-safe
+  const unsigned int (*tab)[256] = tables.t;
   const unsigned char* p = static_cast<const unsigned char*>(data);
   crc = ~crc;
   while (n >= 8) {

@@ -50,6 +50,7 @@ struct LstmTcParams {
   float* gates_seq;        // nullable, indexed like pre: post-activation [g|i|f|o]; may alias pre
   __nv_bfloat16* out_split;  // nullable [2][B*T][out_kp]: the hidden sequence as bf16 hi rows then lo rows,
   int out_kp;                //   i.e. the next layer's tensor-core A operand, ready made
+  int zero_pad;              // gen 2: the threads of units >= H write the K padding of out_split (no separate memset)
   long long pre_dir, pre_row;   // element strides of pre: address = dir*pre_dir + (t*B + b)*pre_row + gate*H + unit
   int n_dir, T, B, H;
   long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
@@ -677,6 +678,12 @@ lstm_tc2_kernel(const LstmTcParams p) {
         vh = (e & 0xffffu) | (o << 16);
         vl = (e >> 16) | (o & 0xffff0000u);
       }
+      if (p.zero_pad && odd && b < B && unit >= H) {
+        // columns [n_dir*H, out_kp) of the operand: n_dir * (32*ncta - H) of them, one pair per idle unit pair (h = 0 here)
+        __nv_bfloat16* oh = p.out_split + ((size_t)b * T + to) * p.out_kp + p.n_dir * H + dir * (ncta * kUnits - H) + (unit - 1 - H);
+        *reinterpret_cast<uint32_t*>(oh) = 0u;
+        *reinterpret_cast<uint32_t*>(oh + (size_t)B * T * p.out_kp) = 0u;
+      }
       if (valid) {
         if (odd && p.out_split) {
           if (HF) split2_bf16(he, ho, vh, vl);
@@ -837,10 +844,8 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   if (out_split) {
     DANET_REQUIRE(out_kp >= n_dir * H && out_kp % 64 == 0 && aligned16(out_split), DANET_E_SHAPE,
                   "lstm_seq: out_split needs a 16-byte aligned buffer with row length %d >= %d, multiple of 64", out_kp, n_dir * H);
-    if (out_kp > n_dir * H)      // zero the K padding of both halves once
-      DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,
-                                   (size_t)2 * B * T, stream));
   }
+  p.zero_pad = 0;
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
@@ -865,11 +870,27 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   const int nb = force ? atoi(force) : (clusters8 <= resident ? 8 : 16);
   // backend 2 (fp16 recurrent state) exists for the 8-per-cluster kernel only; a batch too large for that runs the
   // (more exact) bf16x3 kernel with 16 utterances per cluster instead
-  if (nb != 8) return launch_cluster(lstm_tc_kernel<16>, p, ncta, 16, kThreads, stream);
+  bool pad_memset = false;
   const char* ver = getenv("DANET_LSTM_V");
-  if (ver && atoi(ver) == 1 && !h_fp16) return launch_cluster(lstm_tc_kernel<8>, p, ncta, 8, kThreads, stream);
+  const bool gen1 = nb != 8 || (ver && atoi(ver) == 1 && !h_fp16);
+  if (gen1) {
+    if (out_split && out_kp > n_dir * H)
+      DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,
+                                   (size_t)2 * B * T, stream));
+    return nb != 8 ? launch_cluster(lstm_tc_kernel<16>, p, ncta, 16, kThreads, stream)
+                   : launch_cluster(lstm_tc_kernel<8>, p, ncta, 8, kThreads, stream);
+  }
   if (wh_packed && lstm_tc2_packed_fits(ncta) && !getenv("DANET_LSTM_NOPACK"))
     p.Wh_packed = reinterpret_cast<const uint32_t*>(wh_packed);
+  if (out_split && out_kp > n_dir * H) {
+    // the K padding of the emitted operand must be zero: the generation-2 kernel writes it itself when the idle unit slots
+    // of its last CTA cover it exactly (always for n_dir = 2), otherwise one memset
+    if (out_kp - n_dir * H == n_dir * (ncta * kUnits - H)) p.zero_pad = 1;
+    else pad_memset = true;
+  }
+  if (pad_memset)
+    DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,
+                                 (size_t)2 * B * T, stream));
   return h_fp16 ? launch_cluster(lstm_tc2_kernel<1>, p, ncta, 8, kThreads2, stream)
                 : launch_cluster(lstm_tc2_kernel<0>, p, ncta, 8, kThreads2, stream);
 }

@@ -35,11 +35,12 @@ struct AttParams {
 };
 
 // phase 1 for one time-frequency bin: the R row weights Wt[tf][:]
-template <int MODE>
+// EC: the embedding size when it is known at compile time (register-tiled fast path), 0 = read it from p
+template <int MODE, int EC = 0>
 __device__ __forceinline__ void row_weights(const AttParams& p, int b, long long tf, bool in_range,
                                             const float* __restrict__ v, const float* __restrict__ sAux,
                                             float* __restrict__ w) {
-  const int E = p.E, C = p.C, R = p.R;
+  const int E = EC ? EC : p.E, C = p.C, R = p.R;
   const long long TF = p.TF;
   if (!in_range) {
     for (int r = 0; r < R; ++r) w[r] = 0.f;
@@ -181,7 +182,7 @@ attractor_partial_rt_kernel(const AttParams p) {
       }
     }
     __syncthreads();
-    row_weights<MODE>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * ldw);
+    row_weights<MODE, E>(p, b, tf0 + tid, tid < n_here, sV + tid * ldv, sAux, sW + tid * ldw);
     __syncthreads();
     if (active) {
       for (int tfl = g; tfl < n_here; tfl += G) {

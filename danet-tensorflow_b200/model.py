@@ -442,6 +442,17 @@ class Model(object):
         idle.  `wav` and `out` may be PINNED HOST tensors: each group then copies its own slice in and
         out on its stream, so the PCIe transfers of one group overlap the compute of the others."""
         B, n = wav.shape
+        align = int(getattr(self.encoder, 'TIME_ALIGN', 1) or 1)
+        if align > 1 and K.num_frames(n) % align:
+            # conv-bilstm-v1 needs T % 4 == 0 (the reference pads its batches to LENGTH_ALIGN, main.py:667-668): append
+            # silence up to the next aligned frame count and trim the result back to the 64*T samples of the input
+            if out is not None or not wav.is_cuda:
+                raise ValueError('the encoder needs a frame count that is a multiple of %d (got %d); pass a device tensor '
+                                 'without `out` to have it padded' % (align, K.num_frames(n)))
+            T_in = K.num_frames(n)
+            T_al = T_in + (-T_in) % align
+            padded = torch.nn.functional.pad(wav, (0, K.FFT_STRIDE * (T_al - 1) - n))
+            return self.separate(padded, groups)[..., :K.FFT_STRIDE * T_in].contiguous()
         if groups is None:
             groups = max(1, min(self.PIPELINE_MAX_GROUPS, B // self.PIPELINE_GROUP))
             geo = getattr(self.encoder, '_geometry', None)

@@ -233,6 +233,8 @@ class ConvBiLstmEncoder(Encoder):
     and a bias-free dense layer FFT_SIZE -> F*E.  T must be a multiple of 4 (the reference pads, main.py:667-671).
     Variables are created under tf.layers' names (conv2d, conv2d_1, ..., dense) in the reference's order.
     Inference only: no backward pass is provided for this encoder."""
+    TIME_ALIGN = 4             # two 2x2 max-pools over time: Model.separate pads waveforms to a multiple of 4 frames
+
     def _conv(self, idx, x, k, cout, init=None):
         model = self.model
         nm = '%s/conv2d%s' % (self.name, '' if idx == 0 else '_%d' % idx)

@@ -681,6 +681,27 @@ def test_full_size_configs(D, cfg):
     assert float((again - out).abs().max()) == 0.
 
 
+def test_conv_bilstm_separate_pads_to_frame_alignment(D):
+    """conv-bilstm-v1 needs T % 4 == 0: Model.separate pads the waveform and trims the result; an aligned input goes
+    straight through and equals the oracle's wav -> wav path"""
+    K = D.kernels
+    _set_hparams(D, ENCODER_TYPE='conv-bilstm-v1', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=2)
+    model = D.Model('convsep').build()
+    wav = _shaped_noise(2, 64 * 11, 3)                       # T = 12: aligned
+    out = model.separate(wav)
+    assert out.shape == (2, 2, 64 * 12) and bool(torch.isfinite(out).all())
+    P = {k: v.detach().cpu().double() for k, v in model.params.items()}
+    P['infer_estimator/anchors'] = P['train_estimator/anchors']
+    x = torch.log1p(torch.from_numpy(np.stack([O.stft(w) for w in wav.cpu().numpy()])).abs()).double()
+    V = O.encoder_conv_bilstm(x, P, 20)
+    assert rel(model.encoder(K.stft(wav, want_logmag=True)[1]), V) < TOL
+    wav2 = _shaped_noise(2, 64 * 9 + 17, 4)                  # T = 11: padded to 12 internally
+    T2 = K.num_frames(wav2.shape[1])
+    out2 = model.separate(wav2)
+    assert out2.shape == (2, 2, 64 * T2) and bool(torch.isfinite(out2).all())
+
+
 def test_train_step_reduces_loss(D):
     """cfg 2 training step (anchor + softmax, Adam 3e-4, clip 100) on a fixed batch: the loss goes down"""
     K = D.kernels

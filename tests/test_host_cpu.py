@@ -65,7 +65,7 @@ def test_hparams_load_rejects_bad_keys(D):
 
 def test_registries_hold_reference_names(D):
     H = D.Hyperparameter
-    assert {'lstm-orig', 'bilstm-orig'} <= set(H.encoder_registry)
+    assert {'toy', 'lstm-orig', 'bilstm-orig', 'conv-bilstm-v1'} <= set(H.encoder_registry)   # app/modules.py: every registered encoder
     assert {'truth', 'truth-threshold', 'truth-weighted', 'anchor', 'kmeans'} <= set(H.estimator_registry)
     assert {'dot-sigmoid-orig', 'dot-softmax-orig'} <= set(H.separator_registry)
     with pytest.raises(KeyError):

@@ -1,5 +1,6 @@
 // Library identity, error string, device check.
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace danet {
@@ -14,16 +15,17 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
+  static std::atomic<int> cached{0};
+  int n = cached.load(std::memory_order_relaxed);
+  if (n == 0) {
+    int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+      cached.store(n, std::memory_order_relaxed);
     else
       return 148;
   }
-  return cached;
+  return n;
 }
 
 }  // namespace danet

@@ -10,6 +10,7 @@
 //      (optionally [B,T] -> [T,B] row remap) while the next tile's MMAs run; CTAs pick up further tiles through
 //      cluster launch control (try_cancel of pending CTAs of the same grid).
 #include <cuda.h>
+#include <atomic>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -330,13 +331,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
+  static std::atomic<EncodeTiledFn> cached{nullptr};
+  EncodeTiledFn fn = cached.load(std::memory_order_relaxed);
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
+        q == cudaDriverEntryPointSuccess) {
       fn = reinterpret_cast<EncodeTiledFn>(p);
+      cached.store(fn, std::memory_order_relaxed);
+    }
   }
   return fn;
 }

@@ -18,6 +18,7 @@
 // mbarrier.  No global-memory round trip and no cluster-wide barrier sits on the T-step
 // critical path.
 #include <stdlib.h>
+#include <atomic>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -850,8 +851,10 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
   const int clusters8 = n_dir * ((B + 7) / 8);
-  static int resident_cache[kMaxCta + 1] = {0};
-  int resident = resident_cache[ncta];
+  // per-cluster-size occupancy, queried once; the C-ABI is re-entrant, so the cache is atomic (two threads racing here
+  // both compute the same value and store it)
+  static std::atomic<int> resident_cache[kMaxCta + 1];
+  int resident = resident_cache[ncta].load(std::memory_order_relaxed);
   if (resident == 0) {
     const size_t smem = lstm_tc_smem_bytes(ncta);
     DANET_CUDA(cudaFuncSetAttribute(lstm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -864,7 +867,7 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
       cudaGetLastError();
       resident = num_sms() / (ncta + 2);
     }
-    resident_cache[ncta] = resident;
+    resident_cache[ncta].store(resident, std::memory_order_relaxed);
   }
   const char* force = getenv("DANET_LSTM_NB");
   const int nb = force ? atoi(force) : (clusters8 <= resident ? 8 : 16);

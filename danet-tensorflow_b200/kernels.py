@@ -294,7 +294,7 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
         kp = (n_dir * H + 63) // 64 * 64
         out_split = torch.empty((2, B * T, kp), dtype=torch.bfloat16, device=pre.device)
     _lib.check(lib.danet_lstm_seq_fwd_packed(_p(pre), dir_stride, row_stride, ptrs, 4 * H,
-                                             _p(wh_packed) if be == 1 else None, _p(out), _p(cell),
+                                             _p(wh_packed) if be >= 1 else None, _p(out), _p(cell),
                                              _p(pre) if keep_gates else None, _p(out_split), kp, n_dir, T, B, H,
                                              _p(ws), ws.numel(), be, _stream()), 'lstm_seq')
     _count()

@@ -35,6 +35,7 @@ class Model(object):
         self._twins = {}
         self._graphs = {}
         self._packed = {}                 # weights pre-split for the tensor cores (dropped whenever they change)
+        self._packed_ready = False        # True once every entry exists (built on ONE stream, see _prepare_packed)
         self._last_split = None           # (hidden sequence, its split copy) handed from layer to layer
         self._tape = None                 # training: saved activations per recurrent layer
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
@@ -55,12 +56,24 @@ class Model(object):
             raise ValueError('variable %s has shape %s, requested %s' % (name, tuple(v.shape), shape))
         return v
 
-    def load_params(self, params):
-        """Take weights by reference name (numpy arrays or tensors); the role of main.py:201-206"""
+    def _invalidate(self):
+        """the weights changed (or moved): drop everything derived from them -- the pre-split tensor-core images AND the
+        captured CUDA graphs, which hold raw pointers to those images and to the variables themselves"""
         self._packed = {}
+        self._packed_ready = False
+        self._graphs = {}
+        self._last_split = None
+
+    def load_params(self, params):
+        """Take weights by reference name (numpy arrays or tensors); the role of main.py:201-206.  A variable the model
+        already holds must keep its shape (tf.train.Saver.restore raises on a mismatch)."""
+        self._invalidate()
         for k, v in params.items():
             t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
             t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            if k in self.params and tuple(self.params[k].shape) != tuple(t.shape):
+                raise ValueError('variable %s has shape %s, the restored value %s'
+                                 % (k, tuple(self.params[k].shape), tuple(t.shape)))
             if self._flat is not None and k in self.params:
                 self.params[k].copy_(t)          # keep the flat-buffer views
             else:
@@ -78,9 +91,12 @@ class Model(object):
         from . import tf_bundle
         return tf_bundle.write_bundle(path, {self.TF_SCOPE + k: v.detach().cpu().numpy() for k, v in self.params.items()})
 
-    def load_params_file(self, path):
+    def load_params_file(self, path, strict=True):
         """main.py:201-206: restore from a torch file (`*.pt`) or a TensorFlow checkpoint prefix.  Variables the model
-        does not have (optimiser slots, step counters) are ignored; returns the names that were loaded."""
+        does not have (optimiser slots, step counters) are ignored; returns the names that were loaded.  Like
+        tf.train.Saver.restore (NotFoundError), a model variable the file does not hold is an error -- a checkpoint of
+        another encoder / estimator configuration must not restore partially and report success (`strict=False`: only
+        what matches by name is loaded)."""
         if path.endswith('.pt'):
             params = torch.load(path)
         else:
@@ -88,8 +104,12 @@ class Model(object):
             prefix = path[:-6] if path.endswith('.index') else path
             n = len(self.TF_SCOPE)
             params = {k[n:]: v for k, v in tf_bundle.read_bundle(prefix).items() if k.startswith(self.TF_SCOPE)}
-            if self.params:
-                params = {k: v for k, v in params.items() if k in self.params}
+        if self.params:
+            params = {k: v for k, v in params.items() if k in self.params}
+            missing = sorted(set(self.params) - set(params))
+            if missing and strict:
+                raise KeyError('checkpoint %s does not hold %d of the model\'s %d variables (first: %s)'
+                               % (path, len(missing), len(self.params), missing[0]))
         self.load_params(params)
         return sorted(params)
 
@@ -242,7 +262,7 @@ class Model(object):
         for k in names:
             offs[k] = total
             total += (self.params[k].numel() + 63) // 64 * 64          # 256-byte aligned views
-        self._packed = {}
+        self._invalidate()
         flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         grad = torch.zeros_like(flat)
         for k in names:
@@ -307,8 +327,7 @@ class Model(object):
         """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then the registered optimiser (app/ozers.py), one fused
         launch over the flat parameter buffer"""
         self.step_count += 1
-        self._packed = {}
-        self._graphs = {}                 # captured graphs hold the old packed weights
+        self._invalidate()                # captured graphs hold the old packed weights
         f = self._flat
         opt = hparams.get_optimizer()(hparams.LR)
         if opt['kind'] == 'adam':
@@ -429,6 +448,21 @@ class Model(object):
         out = self.separator(mix_pwr, attrs, embed_flat, s_mixed_signals=mix, want=(want,))
         return out[want]
 
+    def _prepare_packed(self, F):
+        """Build every cached weight image (split input rows, packed recurrent rows, column sums) on the CURRENT stream
+        with one 4-frame dry run of the encoder.  `separate` calls this before it forks its stream groups: the groups
+        share the cache, and an entry built on group 0's stream would be read by the other groups' kernels with no
+        ordering between the streams."""
+        if self._packed_ready or self._tape is not None:
+            return
+        T0 = max(4, int(getattr(self.encoder, 'TIME_ALIGN', 1) or 1))
+        pending, self._stagger_pending = self._stagger_pending, False
+        self._last_split = None
+        self.encoder(torch.zeros((1, T0, F), dtype=torch.float32, device=self.device))
+        self._last_split = None
+        self._stagger_pending = pending
+        self._packed_ready = True
+
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
     PIPELINE_MAX_GROUPS = 4
 
@@ -491,6 +525,7 @@ class Model(object):
             run(0, B)
             return out
         main = torch.cuda.current_stream()
+        self._prepare_packed(hparams.FEATURE_SIZE)      # shared weight images: built before the fork, on one stream
         fork = main.record_event()
         streams = self._side_streams(groups)
         prev = None

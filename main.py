@@ -85,6 +85,9 @@ def main(argv=None):
         print('%s: loss=%.4e SNR=%.3f dB' % (subset, loss / max(n, 1), snr / max(n, 1)))
 
     if args.mode == 'train':
+        if hparams.LR_DECAY_TYPE not in (None, 'adaptive', 'fixed'):
+            raise ValueError('Unknown LR_DECAY_TYPE "%s"' % hparams.LR_DECAY_TYPE)          # main.py:449-451
+        best_loss, stale_epochs = float('inf'), 0
         for epoch in range(1, args.num_epoch + 1):
             loss, snr, n = 0., 0., 0
             for src in batches(dataset, 'train', B, C, hparams.MAX_TRAIN_LEN):
@@ -95,6 +98,20 @@ def main(argv=None):
                 sys.stdout.write('.')
                 sys.stdout.flush()
             print('\nEpoch %d/%d: loss=%.4e SNR=%.3f dB LR=%g' % (epoch, args.num_epoch, loss / n, snr / n, hparams.LR))
+            # learning-rate schedule (main.py:438-459): 'adaptive' counts epochs without a new best mean loss, 'fixed'
+            # counts every epoch; after NUM_EPOCH_PER_LR_DECAY of them the rate is multiplied by LR_DECAY
+            if hparams.LR_DECAY_TYPE == 'adaptive':
+                if loss / n < best_loss:
+                    best_loss, stale_epochs = loss / n, 0
+                else:
+                    stale_epochs += 1
+            elif hparams.LR_DECAY_TYPE == 'fixed':
+                stale_epochs += 1
+            if hparams.LR_DECAY_TYPE is not None and stale_epochs == hparams.NUM_EPOCH_PER_LR_DECAY:
+                stale_epochs = 0
+                old_lr = model.get_learn_rate()
+                model.set_learn_rate(old_lr * hparams.LR_DECAY)
+                print('[LR %f -> %f]' % (old_lr, model.get_learn_rate()))
             if not args.no_save_on_epoch:
                 model.save_params('saves_%s_e%d.pt' % (args.name, epoch))
             if not args.no_valid_on_epoch:

@@ -1,0 +1,254 @@
+"""
+Parity at the BENCHMARKED sizes: embedding, attractors, masks, separated spectra and
+separated waveforms of the CUDA path against the CPU oracle (fp64) on the bench's own synthetic mixtures, at the
+shapes BASELINE.json names -- not only properties.  Gate: 1e-3 max-norm relative (north_star), masks absolute
+(their scale is 1); discrete choices (anchor subset, PIT permutation) must be equal.
+
+  cfg 2   B x 4 s, T = 501, 4 x (300+300), E = 20, anchor, softmax -- backend 1 (bf16x3) AND backend 2 (fp16
+          recurrent state, what bench.py times), eager and the graphed / grouped `separate_host` call
+  cfg 2v  the "3 x 600" variant (3 layers, 600 = 300 + 300 wide)
+  cfg 4   3 speakers, 8 s, T = 1001, E = 40: anchor, and k-means seeded by the anchor attractors
+  cfg 5   one 30 s stream, T = 3751
+  cfg 1   the toy dataset's real shape [2,2,128,129], `truth` estimator, both separators (train graph)
+The oracle runs in float64 on a few utterances (seconds on the box's host cores).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import danet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def D():
+    import danet_tensorflow_b200 as D
+    D._lib.load()
+    assert D._lib.load().danet_check_device() == 0, D._lib.load().danet_last_error_string()
+    return D
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def absdiff(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max())
+
+
+def _configure(D, backend, fp16, **over):
+    kw = dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+              SEPARATOR_TYPE='dot-softmax-orig')
+    kw.update(over)
+    D.hparams.__dict__.clear()
+    D.hparams.__dict__.update(D.Hyperparameter().__dict__)
+    D.hparams.load(kw)
+    D.hparams.digest()
+    D.kernels.DEFAULT_BACKEND = backend
+    D.Model.RECURRENT_FP16 = bool(fp16)
+
+
+@pytest.fixture(autouse=True)
+def _restore_defaults():
+    yield
+    import danet_tensorflow_b200 as D
+    D.kernels.DEFAULT_BACKEND = 1
+    D.Model.RECURRENT_FP16 = True
+
+
+def _product_stages(D, model, wav):
+    """the inference path stage by stage through the plugin surface (what Model.separate runs per stream group)"""
+    K = D.kernels
+    mix, logmag = K.stft(wav, want_logmag=True)
+    B, T, F = mix.shape
+    embed = model.encoder(logmag)
+    flat = embed.view(B, T * F, -1)
+    attrs = model.infer_estimator(embed, s_embed_flat=flat)
+    out = model.separator(None, attrs, flat, s_mixed_signals=mix, want=('sep', 'masks'))
+    return dict(embed=embed, attrs=attrs, masks=out['masks'], sep=out['sep'])
+
+
+def _check_against_oracle(got, wavs, ref_wav, ref_sig, aux, n_ref, what):
+    errs = dict(
+        embed=rel(got['embed'][:n_ref], aux['embed']),
+        attrs=rel(got['attrs'][:n_ref], aux['attrs']),
+        masks=absdiff(got['masks'][:n_ref], aux['masks']),
+        spectra=rel(torch.view_as_real(got['sep'][:n_ref]), torch.view_as_real(ref_sig)),
+        wav=rel(wavs[:n_ref], ref_wav))
+    print('%s: max-norm errors vs the fp64 oracle: %s' % (what, ', '.join('%s %.2e' % kv for kv in errs.items())))
+    for k, v in errs.items():
+        assert v < TOL, (what, k, v, errs)
+    return errs
+
+
+@pytest.mark.parametrize('backend,fp16', [(1, False), (1, True), (0, False)],
+                         ids=['tcgen05-bf16x3', 'tcgen05-fp16-state', 'fp32-simt'])
+def test_cfg2_embeddings_masks_spectra_waveforms(D, backend, fp16):
+    """configs[1]: the bench's own mixtures (synth_mixtures, seed 1337), T = 501, 4 layers -- every tensor north_star
+    names, for the precision the headline number is measured with (fp16 recurrent state) and for bf16x3"""
+    import bench
+    B, n_ref = (16, 4) if backend == 1 else (4, 2)
+    _configure(D, backend, fp16, BATCH_SIZE=B)
+    wav_np = bench.synth_mixtures(B, bench.N_SAMPLES, 1337)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav_np[:n_ref], P, dtype=torch.float64)
+    model = D.Model('full-cfg2').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    wav = torch.from_numpy(wav_np).cuda()
+    got = _product_stages(D, model, wav)
+    assert got['embed'].shape == (B, 501, 129, 20)
+    wavs = model.separate(wav)                                   # 2 stream groups at B = 16
+    _check_against_oracle(got, wavs, ref_wav, ref_sig, aux, n_ref, 'cfg2 backend %d fp16 %d' % (backend, fp16))
+    if backend == 1:
+        # the call bench.py times as `e2e`: pinned host buffers, CUDA graph, stream groups
+        wav_host = torch.from_numpy(wav_np).pin_memory()
+        out_host = torch.empty((B, 2, 64 * 501), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            model.separate_host(wav_host, out_host)
+            torch.cuda.synchronize()
+        assert rel(out_host[:n_ref], ref_wav) < TOL
+        assert float((out_host.cuda() - wavs).abs().max()) == 0.
+
+
+@pytest.mark.parametrize('fp16', [False, True], ids=['bf16x3', 'fp16-state'])
+def test_cfg2_three_layer_variant(D, fp16):
+    """the "BiLSTM-3x600" variant BASELINE.json names (ENCODER_LAYERS = 3, 300 + 300 units per layer)"""
+    import bench
+    B = 2
+    _configure(D, 1, fp16, BATCH_SIZE=B, ENCODER_LAYERS=3)
+    wav_np = bench.synth_mixtures(B, bench.N_SAMPLES, 77)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64, n_layers=3)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav_np, P, dtype=torch.float64, n_layers=3)
+    model = D.Model('full-3x600').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    wav = torch.from_numpy(wav_np).cuda()
+    got = _product_stages(D, model, wav)
+    assert not any('lstm3' in k for k in model.params)
+    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, B, '3x600 fp16 %d' % fp16)
+
+
+@pytest.mark.parametrize('est', ['anchor', 'kmeans'])
+def test_cfg4_three_speakers_8s(D, est):
+    """configs[3]: 3 speakers, 8 s (T = 1001), E = 40; anchor estimator (P = 20 subsets) and the k-means plugin
+    (5 Lloyd iterations from the anchor attractors; the plugin has no reference twin, its oracle is our restatement)"""
+    import bench
+    B, n_ref, C, E, n = 4, 2, 3, 40, 64000
+    _configure(D, 1, True, BATCH_SIZE=B, MAX_N_SIGNAL=C, EMBED_SIZE=E, TRAIN_ESTIMATOR_METHOD=est,
+               INFER_ESTIMATOR_METHOD=est)
+    wav_np = bench.synth_sources(B, n, 4242, C).sum(1).astype(np.float32)
+    P = O.reference_init(1337, embed=E, estimators=('infer_estimator',), dtype=torch.float64)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav_np[:n_ref], P, C=C, embed=E, dtype=torch.float64,
+                                                 infer_est='anchor' if est == 'anchor' else 'kmeans-anchor-init')
+    model = D.Model('full-cfg4').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    wav = torch.from_numpy(wav_np).cuda()
+    got = _product_stages(D, model, wav)
+    assert got['embed'].shape == (B, 1001, 129, E) and got['attrs'].shape == (B, C, E)
+    if est == 'anchor':
+        _, _, sim, choice = O.estimator_anchor(aux['embed'], P['infer_estimator/anchors'], C, return_all=True)
+        gchoice = D.kernels.attractor_anchor(got['embed'], model.params['train_estimator/anchors'], C, return_all=True)[3]
+        assert np.array_equal(gchoice[:n_ref].cpu().numpy(), choice.numpy())
+    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, n_ref, 'cfg4 ' + est)
+
+
+def test_cfg5_30s_stream(D):
+    """configs[4]: one 30 s utterance (T = 3751), anchor estimator + iSTFT -- 15 004 dependent recurrent steps"""
+    import bench
+    n = 240000
+    _configure(D, 1, True, BATCH_SIZE=1)
+    wav_np = bench.synth_mixtures(1, n, 99)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav_np, P, dtype=torch.float64)
+    model = D.Model('full-cfg5').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    wav = torch.from_numpy(wav_np).cuda()
+    got = _product_stages(D, model, wav)
+    assert got['embed'].shape == (1, 3751, 129, 20)
+    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, 1, 'cfg5')
+
+
+@pytest.mark.parametrize('sep', ['dot-softmax-orig', 'dot-sigmoid-orig'])
+@pytest.mark.parametrize('backend', [0, 1])
+def test_cfg1_toy_dataset_real_shape(D, sep, backend):
+    """configs[0] exactly as the reference feeds it (app/datasets/dataset.py:55-59, main.py:417-421):
+    RandomState(1337).rand(4,128,129) as complex spectra [2,2,128,129], bilstm-orig, `truth` estimator on the train
+    side, anchor on the infer side, both separators -- the whole train/valid/infer fetch list"""
+    _configure(D, backend, False, BATCH_SIZE=2, TRAIN_ESTIMATOR_METHOD='truth', INFER_ESTIMATOR_METHOD='anchor',
+               SEPARATOR_TYPE=sep)
+    data = np.random.RandomState(1337).rand(4, 128, 129).astype(np.float32)
+    src_np = data.astype(np.complex64).reshape(2, 2, 128, 129)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64)
+    ref = O.model_forward(torch.from_numpy(src_np).to(torch.complex128), P, encoder='bilstm-orig', train_est='truth',
+                          infer_est='anchor', sep=sep, embed=20)
+    model = D.Model('full-cfg1').build()
+    model.load_params(P)
+    out = model.train_forward(torch.from_numpy(src_np).cuda())
+    assert rel(out['embed'], ref['embed']) < TOL
+    assert rel(out['attrs'], ref['attrs']) < TOL
+    assert rel(out['attrs_valid'], ref['attrs_valid']) < TOL
+    assert absdiff(out['masks'], ref['masks']) < TOL
+    assert absdiff(out['masks_valid'], ref['masks_valid']) < TOL
+    assert rel(out['sep_pwr'], ref['sep_pwr']) < TOL
+    assert np.array_equal(out['perm_idx'].cpu().numpy(), ref['perm_idx'].numpy())
+    assert rel(torch.view_as_real(out['output']), torch.view_as_real(ref['output'])) < TOL
+    assert rel(torch.view_as_real(out['infer_signals']), torch.view_as_real(ref['infer_signals'])) < TOL
+    for k in ('train_loss', 'train_snr', 'valid_loss', 'valid_snr'):
+        assert abs(float(out[k]) - float(ref[k])) <= TOL * max(1., abs(float(ref[k]))), (k, float(out[k]), float(ref[k]))
+
+
+def test_clip_sgd(D):
+    """danet_clip_sgd against clip_by_value + tf.train.GradientDescentOptimizer (main.py:359-363, app/ozers.py:9-12),
+    with the 1/world gradient scale of the sharded step applied before the clip"""
+    K = D.kernels
+    rs = np.random.RandomState(8)
+    n = 100003
+    p0, g0 = rs.standard_normal(n).astype(np.float32), (rs.standard_normal(n) * 80).astype(np.float32)
+    for scale in (1., .5):
+        params, grads = {'w': torch.from_numpy(p0).double()}, {'w': torch.from_numpy(g0).double() * scale}
+        pg = torch.from_numpy(p0).cuda()
+        for _ in range(3):
+            O.clip_sgd_step(params, grads, lr=3e-4, clip=100.)
+            K.clip_sgd(pg, torch.from_numpy(g0).cuda(), 3e-4, clip=100., grad_scale=scale)
+        assert rel(pg, params['w']) < 1e-6
+    assert float((np.abs(g0) > 100).mean()) > 0.1                # the clip was exercised
+
+
+def test_sgd_train_step_matches_oracle_autograd(D):
+    """one whole training step with the `sgd` optimiser: parameters after the step against oracle forward +
+    torch autograd + clip_sgd_step (OPTIMIZER_TYPE = 'sgd' is a registered choice, app/ozers.py:9-12)"""
+    _configure(D, 1, False, BATCH_SIZE=2, TRAIN_ESTIMATOR_METHOD='truth-weighted', INFER_ESTIMATOR_METHOD='anchor',
+               SEPARATOR_TYPE='dot-sigmoid-orig', OPTIMIZER_TYPE='sgd', LR=1e-3)
+    rs = np.random.RandomState(3)
+    src_np = ((rs.standard_normal((2, 2, 24, 129)) + 1j * rs.standard_normal((2, 2, 24, 129))) * 5).astype(np.complex64)
+    P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ref = O.model_forward(torch.from_numpy(src_np).to(torch.complex128), Pg, encoder='bilstm-orig',
+                          train_est='truth-weighted', infer_est='anchor', sep='dot-sigmoid-orig', embed=20)
+    ref['train_loss'].backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
+    new = {k: v.detach().clone() for k, v in P.items()}
+    O.clip_sgd_step(new, grads, lr=1e-3, clip=100.)
+    model = D.Model('sgd').build()
+    model.load_params(P)
+    out = model.train_step(torch.from_numpy(src_np).cuda())
+    assert abs(float(out['loss']) - float(ref['train_loss'])) <= TOL * abs(float(ref['train_loss']))
+    for k in ('encoder/lstm0_fwd/LSTM/linear/W', 'encoder/lstm3_bwd/LSTM/linear/B', 'encoder/output/W'):
+        step_ref = (new[k] - P[k]).numpy()
+        step_got = model.params[k].detach().cpu().double().numpy() - P[k].numpy()
+        assert np.abs(step_got - step_ref).max() <= 2e-3 * np.abs(step_ref).max() + 1e-9, k

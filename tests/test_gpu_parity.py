@@ -267,6 +267,14 @@ def test_lstm_seq_packed_weights(K, backend, n_dir, B, T, H):
     a = K.lstm_seq(pre, Wg, I, T, B, H, backend=backend)
     b, b_split = K.lstm_seq(pre, Wg, I, T, B, H, backend=backend, wh_packed=packed, want_split=True)
     assert torch.equal(a, b)
+    # the packed image is what the kernel reads, on BOTH tensor-core backends: with the fp32 recurrent rows zeroed the
+    # result must not move (a run that silently fell back to splitting the fp32 rows in its prologue would return the
+    # recurrence of Wh = 0 here)
+    Wz = [w.clone() for w in Wg]
+    for w in Wz:
+        w[I:].zero_()
+    assert torch.equal(K.lstm_seq(pre, Wz, I, T, B, H, backend=backend, wh_packed=packed), a)
+    assert not torch.equal(K.lstm_seq(pre, Wz, I, T, B, H, backend=backend), a)
     kp = b_split.shape[-1]
     hi, lo = b_split[0].float(), b_split[1].float()
     assert rel((hi + lo)[:, :n_dir * H], a.reshape(B * T, n_dir * H)) < 1e-5

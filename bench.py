@@ -69,7 +69,7 @@ def reference_params(seed=1337):
 
 
 def cpu_reference_rate(wav, threads, repeats=1):
-    """mixtures/sec of the CPU restatement (oracle) on `wav` [b, N], and its separated waveforms"""
+    """mixtures/sec of the CPU restatement (oracle) on `wav` [b, N], its separated waveforms and intermediate tensors"""
     from oracle import danet_oracle as O
     torch.set_num_threads(threads)
     P = reference_params()
@@ -78,9 +78,10 @@ def cpu_reference_rate(wav, threads, repeats=1):
     out = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = O.separate_waveforms(wav, P, dtype=torch.float32)[0]
+        out, sig, aux = O.separate_waveforms(wav, P, dtype=torch.float32)
         best = min(best, time.perf_counter() - t0)
-    return wav.shape[0] / best, best, np.asarray(out)
+    aux = dict(aux, sig=sig)
+    return wav.shape[0] / best, best, np.asarray(out), aux
 
 
 class ClockSampler(threading.Thread):
@@ -129,46 +130,93 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.rows)}
 
 
+def cpu_reference_train_rate(src_np, threads, repeats=2):
+    """mixtures/sec of ONE training step of the CPU restatement on complex source spectra [b,C,T,F]: forward of the train
+    graph (main.py:233-337), torch autograd in place of tf.gradients (main.py:357-358), clip + Adam (main.py:359-363)"""
+    from oracle import danet_oracle as O
+    torch.set_num_threads(threads)
+    P = O.reference_init(1337, encoder='bilstm-orig', embed=EMBED, estimators=('train_estimator',), dtype=torch.float32)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    m = {k: torch.zeros_like(v) for k, v in P.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in P.items()}
+    src = torch.from_numpy(src_np).to(torch.complex64)
+    best = float('inf')
+    for it in range(repeats):
+        t0 = time.perf_counter()
+        out = O.model_forward(src, Pg, encoder='bilstm-orig', train_est='anchor', infer_est='anchor',
+                              sep='dot-softmax-orig', embed=EMBED)
+        out['train_loss'].backward()
+        with torch.no_grad():
+            cur = {k: p.detach().clone() for k, p in Pg.items()}
+            O.clip_adam_step(cur, {k: p.grad for k, p in Pg.items()}, m, v2, it + 1)
+            for k, p in Pg.items():
+                p.copy_(cur[k])
+                p.grad = None
+        best = min(best, time.perf_counter() - t0)
+    return src.shape[0] / best, best
+
+
+def source_spectra(batch, seed):
+    """complex source spectra [b,C,T,F] of the synthetic sources (host STFT of the oracle: the training step's input)"""
+    from oracle import danet_oracle as O
+    w = synth_sources(batch, N_SAMPLES, seed)
+    return np.stack([[O.stft(x) for x in u] for u in w]).astype(np.complex64)
+
+
 def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores.  TensorFlow 1.x cannot be
+    installed in this image (no wheel, no network), so the op-for-op torch-CPU restatement in oracle/
+    stands in for it (`cpu_baseline.kind = "port"`).  Same config / metric / unit as the repo arm, --steps / --warmup
+    honoured; every step is one full batch of the workload."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    b = args.ref_batch
+    b = args.batch
     wav = synth_mixtures(b, N_SAMPLES, 1337)
     times = []
     P = reference_params()
     from oracle import danet_oracle as O
     torch.set_num_threads(threads)
     O.separate_waveforms(wav[:1, :2048], P, dtype=torch.float32)
-    steps = max(1, min(args.steps, args.ref_steps))
-    for _ in range(steps):
+    for _ in range(max(args.warmup, 0)):
+        O.separate_waveforms(wav, P, dtype=torch.float32)
+    for _ in range(args.steps):
         t0 = time.perf_counter()
         O.separate_waveforms(wav, P, dtype=torch.float32)
         times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     val = b / (ms / 1e3)
+    train = None
+    if args.train_steps > 0:
+        nb = args.cpu_train_mixtures
+        rate, secs = cpu_reference_train_rate(source_spectra(nb, 1337), threads)
+        train = {'value': rate, 'unit': 'mixtures/s', 'ms_per_step': 1e3 * secs * b / nb, 'cores': threads, 'kind': 'port',
+                 'sample': '%d of the %d mixtures of one training step, best of 2 (%.1f s each): oracle forward + torch '
+                           'autograd + clip/Adam' % (nb, b, secs)}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'mixtures/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(b, 'cpu'),
+        'config': workload_config(b),
+        'where': 'host cores (torch-CPU fp32, %d threads)' % threads,
         'cpu_baseline': {'value': val, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d mixtures of 4 s per step, %d steps; torch-CPU fp32 restatement of the TF1 '
-                                   'graph (TensorFlow 1.x is not installable here)' % (b, steps)},
+                         'sample': '%d mixtures of 4 s per step (one full batch), %d steps after %d warm-up; torch-CPU fp32 '
+                                   'restatement of the TF1 graph (TensorFlow 1.x is not installable here)'
+                                   % (b, args.steps, args.warmup)},
         'e2e': {'value': val, 'unit': 'mixtures/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'train': train,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, where, recurrent_fp16=False):
+def workload_config(batch):
+    """ONE dict for both arms (the driver compares them key by key); what differs between the arms -- where it runs, the
+    arithmetic, the schedule -- is reported under separate top-level keys"""
     return {'workload': 'cfg2-infer: wav->STFT->logmag->BiLSTM 4x(300+300)->anchor(6)->softmax mask x mix->iSTFT',
             'batch_per_gpu': batch, 'n_speakers': N_SPK, 'samples': N_SAMPLES, 'frames': 501, 'fft': 256,
             'hop': 64, 'embed': EMBED, 'estimator': 'anchor', 'separator': 'dot-softmax-orig',
-            'parallelism': 'utterance-sharded, no collective', 'l2': 'flushed between timed steps', 'where': where,
-            'schedule': 'CUDA graph, 4 stream groups of 8 utterances, staggered',
-            'arithmetic': 'fp32 in / out; tensor-core products on bf16 hi/lo splits (3 products, fp32 accumulate)' +
-                          ('; the recurrent product takes h_{t-1} as one fp16 value x fp16 hi/lo weights'
-                           if recurrent_fp16 else '')}
+            'parallelism': 'utterance-sharded, no collective',
+            'l2': 'flushed between timed steps (GPU arm: 256 MB write before every step)'}
 
 
 def main():
@@ -179,18 +227,18 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='mixtures per GPU per step')
     ap.add_argument('--backend', type=int, default=None, help='0 = fp32 SIMT, 1 = tcgen05')
-    ap.add_argument('--ref-batch', type=int, default=32)
-    ap.add_argument('--ref-steps', type=int, default=5)
     ap.add_argument('--cpu-baseline-mixtures', type=int, default=32)
+    ap.add_argument('--cpu-train-mixtures', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1 = replay the step from a CUDA graph (default), 0 = eager')
-    ap.add_argument('--train-steps', type=int, default=3, help='timed training steps for the extra "train" key (0 = skip)')
+    ap.add_argument('--train-steps', type=int, default=10, help='timed training steps for the "train" key (0 = skip)')
     ap.add_argument('--extras', type=int, default=1,
                     help='1 = also time BASELINE.json configs[3] (3 speakers, 8 s, E = 40, k-means) and configs[4] (one 30 s '
                          'stream, latency) on rank 0 and report them under "other_configs"')
     ap.add_argument('--recurrent-fp16', type=int, default=1,
                     help='1 (default) = inference carries h into the recurrent product as fp16 (C-ABI backend 2, ~1e-4 of the '
-                         'embedding scale); 0 = bf16 hi/lo everywhere (~1e-5)')
+                         'embedding scale); 0 = bf16 hi/lo everywhere (~1e-5).  The other setting is timed as well and '
+                         'reported under "precision_ab"')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -206,6 +254,8 @@ def main():
         raise RuntimeError('bench.py needs a CUDA device (no CPU fallback for the product path)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    full_affinity = os.sched_getaffinity(0)
+    numa = D.shard.bind_to_local_numa(local)          # before any pinned allocation: host buffers on the GPU's own node
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
@@ -228,7 +278,7 @@ def main():
     out_host = torch.empty((B, N_SPK, 64 * T), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    # instrument our kernels with events on the launching stream (used in the eager pass only)
+    # instrument our kernels with events on the launching stream (used in the eager passes only)
     kernel_events = {}
 
     class Timed(object):
@@ -247,7 +297,8 @@ def main():
             kernel_events.setdefault(name, []).append((e0, e1))
             return r
         setattr(K, name, timed)
-    for nm in ('lstm_seq', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'mask_cmul_istft', 'gemm_split', 'split_operand', 'mean'):
+    for nm in ('lstm_seq', 'lstm_seq_bwd', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'mask_cmul_istft', 'gemm_split',
+               'split_operand', 'mean'):
         instrument(nm)
 
     def barrier():
@@ -295,20 +346,70 @@ def main():
     per_kernel = {k: [a.elapsed_time(b) for a, b in v] for k, v in kernel_events.items()}
     lstm_ms = per_kernel.get('lstm_seq', [])
     clocks = sampler.stop()
+    got_e2e = out_host.clone()
 
-    # ---- extra: the training step of the same config (forward + backward + gradient all-reduce + clip/Adam)
+    # ---- the other precision setting of the recurrent product, timed the same way (device-resident and end to end)
+    precision_ab = None
+    if K.DEFAULT_BACKEND == 1 and args.graph:
+        other = not D.Model.RECURRENT_FP16
+        D.Model.RECURRENT_FP16 = other
+        model._invalidate()
+        for _ in range(3):
+            step_dev()
+            step_e2e()
+        torch.cuda.synchronize()
+        ab_dev = timed_loop(step_dev, args.steps)
+        ab_e2e = timed_loop(step_e2e, args.steps)
+        precision_ab = {'recurrent_fp16': int(other), 'value': B * world * args.steps / (ab_dev / 1e3),
+                        'e2e': B * world * args.steps / (ab_e2e / 1e3), 'unit': 'mixtures/s',
+                        'ms_per_step': ab_dev / args.steps,
+                        'what': 'the same step with the recurrent product ' +
+                                ('taking h as one fp16 value' if other else 'on bf16 hi/lo pairs only (bf16x3 everywhere)')}
+        D.Model.RECURRENT_FP16 = not other
+        model._invalidate()
+
+    # ---- parity of every tensor north_star names, on the timed batch: stage-by-stage eager pass of the product path
+    def product_stages(n):
+        mix, logmag = K.stft(wav_dev[:n], want_logmag=True)
+        embed = model.encoder(logmag)
+        flat = embed.view(n, T * 129, EMBED)
+        attrs = model.infer_estimator(embed, s_embed_flat=flat)
+        o = model.separator(None, attrs, flat, s_mixed_signals=mix, want=('sep', 'masks'))
+        return embed.cpu().numpy(), o['masks'].cpu().numpy(), torch.view_as_real(o['sep']).cpu().numpy()
+
+    # ---- the training step of the same config (forward + backward + bucketed gradient all-reduce + clip/Adam)
     train = None
     if args.train_steps > 0:
         src = K.stft(torch.from_numpy(synth_sources(B, N_SAMPLES, 1337 + rank)).to(dev))     # [B,C,T,F] complex
-        for _ in range(2):
+        for _ in range(3):
             model.train_step(src)
+        model.TIME_ALLREDUCE = True
+        model._ar_events = []
         K.launches = 0
+        kernel_events.clear()
+        Timed.on = True
         ms_train = timed_loop(lambda: model.train_step(src), args.train_steps)
+        Timed.on = False
+        model.TIME_ALLREDUCE = False
+        ar_ms = [a.elapsed_time(b) for a, b in model._ar_events]
+        ar_exposed = D.shard.max_over_ranks(float(np.mean(ar_ms)) if ar_ms else 0., dev)
+        bptt = [a.elapsed_time(b) for a, b in kernel_events.get('lstm_seq_bwd', [])]
+        fwd_l = [a.elapsed_time(b) for a, b in kernel_events.get('lstm_seq', [])]
+        n_param = int(model._flat['grad'].numel())
         train = {'value': B * world * args.train_steps / (ms_train / 1e3), 'unit': 'mixtures/s',
-                 'ms_per_step': ms_train / args.train_steps, 'steps': args.train_steps,
-                 'gpu_launches': K.launches,
-                 'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (tcgen05 cluster BPTT + tcgen05 dW/dX products), '
-                         'one NCCL all-reduce of the flat gradient buffer (N > 1), fused clip + Adam'}
+                 'ms_per_step': ms_train / args.train_steps, 'steps': args.train_steps, 'n_gpus': world,
+                 'global_batch': B * world, 'gpu_launches': K.launches // args.train_steps,
+                 'allreduce_ms_exposed': ar_exposed, 'allreduce_bytes': 4 * n_param,
+                 'allreduce': 'NCCL, 5 buckets in backward completion order (projection + anchors, L3 .. L0), each started '
+                              'on the stream that produced it; exposed = what the step still waits for after the backward',
+                 'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (tcgen05 cluster BPTT + tcgen05 dW/dX '
+                         'products), bucketed gradient all-reduce (N > 1), fused clip + Adam'}
+        if bptt:
+            bflops = 2. * 2 * B * HDIM * 4 * HDIM * T           # dh = da * Wh^T, both directions, per launch
+            bms = float(np.mean(bptt))
+            train['roofline'] = {'bound': 'tensor', 'kernel': 'lstm_seq_bwd (BPTT, one launch per layer)',
+                                 'achieved': bflops / (bms * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'ms_per_launch': bms,
+                                 'launches_per_step': N_LAYERS, 'forward_recurrence_ms_per_launch': float(np.mean(fwd_l)) if fwd_l else None}
 
     # ---- extra: the other single-GPU configurations of BASELINE.json (parity cases in tests/, timed here for the record)
     other = None
@@ -377,8 +478,10 @@ def main():
                 'timed_in': 'eager single-stream pass of the same %d steps (%.3f ms/step); the headline value '
                             'replays the step from a CUDA graph with 4 staggered stream groups' % (args.steps, ms_eager / args.steps),
                 'note': 'algorithmic fp32 flops 2*n_dir*B*H*4H*T; the kernel is bound by the latency of T dependent steps '
-                        '(per step: ~540 cycles of MMAs streaming Wh out of tensor memory, ~550 of epilogue, ~620 of DSMEM '
-                        'exchange of h; profiles/r01_lstm_phase_cycles_v4_gen2.txt), not by tensor throughput'}
+                        '(MMA issue, epilogue and DSMEM exchange of h in series; profiles/r02_lstm_phase_cycles*.txt), '
+                        'not by tensor throughput'}
+    if train is not None and 'roofline' in train:
+        train['roofline'].update(peak=peak_tf, frac=train['roofline']['achieved'] / peak_tf)
 
     # the other kernels of the step against their own rooflines (algorithmic bytes / flops from DESIGN.md section 6)
     hbm = peaks.get('hbm_gbs', 6650.)
@@ -405,41 +508,67 @@ def main():
                             'frac': ach / hbm, 'note': note})
         else:
             n_calls = len(per_kernel[name]) // args.steps
-            flops = 2. * B * T * (129 * 2400 + 3 * 600 * 2400 + 600 * 2580)          # logical fp32 flops per step
+            gflops = 2. * B * T * (129 * 2400 + 3 * 600 * 2400 + 600 * 2580)          # logical fp32 flops per step
             tot_ms = ms * n_calls
-            ach = flops / (tot_ms * 1e-3) / 1e12
+            ach = gflops / (tot_ms * 1e-3) / 1e12
             kernels.append({'kernel': name, 'bound': 'tensor', 'ms_per_step': tot_ms, 'launches_per_step': n_calls,
                             'achieved': ach, 'issued': 3 * ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                             'frac_issued': 3 * ach / peak_tf,
                             'note': note + '; "issued" counts the 3 bf16 products behind every fp32-grade product'})
 
     cpu_baseline, parity = None, None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # "on rank 0 at N = 1 only": all host cores belong to this process
+        os.sched_setaffinity(0, full_affinity)
         threads = os.cpu_count() or 1
-        nb = args.cpu_baseline_mixtures
-        rate, secs, ref_out = cpu_reference_rate(wav_np[:nb], threads, repeats=3)
+        nb = min(args.cpu_baseline_mixtures, B)
+        rate, secs, ref_out, aux = cpu_reference_rate(wav_np[:nb], threads, repeats=3)
         cpu_baseline = {'value': rate, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
                         'sample': '%d of the %d mixtures of one step, best of 3 (%.1f s each); torch-CPU fp32 restatement of '
                                   'the TF1 graph' % (nb, B, secs)}
-        # the checker at work on the timed configuration: separated waveforms of the LAST timed e2e step vs the oracle
-        got = out_host[:nb].numpy()
-        parity = {'max_rel_err': float(np.abs(got - ref_out).max() / np.abs(ref_out).max()), 'tolerance': 1e-3,
-                  'what': 'separated waveforms of the e2e step vs the CPU oracle (fp32) on the same %d mixtures, '
-                          'max-norm relative' % nb}
+        # the checker at work on the timed configuration: every tensor north_star names, product vs the fp32 CPU oracle
+        # on the same mixtures (the fp64 comparison is tests/test_gpu_fullsize.py)
+        npar = min(nb, 8)
+        g_embed, g_masks, g_sep = product_stages(npar)
+        r_embed, r_masks = aux['embed'][:npar].numpy(), aux['masks'][:npar].numpy()
+        r_sep = torch.view_as_real(aux['sig'][:npar]).numpy()
+        got = got_e2e[:nb].numpy()
 
+        def mx(a, b, relative=True):
+            return float(np.abs(a - b).max() / (np.abs(b).max() if relative else 1.))
+        parity = {'tolerance': 1e-3, 'recurrent_fp16': int(D.Model.RECURRENT_FP16),
+                  'embedding': mx(g_embed, r_embed), 'masks_abs': mx(g_masks, r_masks, False),
+                  'spectra': mx(g_sep, r_sep), 'waveforms_e2e': mx(got, ref_out), 'max_rel_err': mx(got, ref_out),
+                  'what': 'max-norm (relative to the largest reference entry; masks absolute) against the fp32 CPU oracle: '
+                          'embedding / masks / separated spectra on the first %d mixtures of the timed batch, waveforms of '
+                          'the LAST timed e2e step on %d' % (npar, nb)}
+        if train is not None:
+            nt = args.cpu_train_mixtures
+            trate, tsecs = cpu_reference_train_rate(source_spectra(nt, 1337), threads)
+            train['cpu_baseline'] = {'value': trate, 'unit': 'mixtures/s', 'cores': threads, 'kind': 'port',
+                                     'sample': '%d of the %d mixtures of one training step, best of 2 (%.1f s each): oracle '
+                                               'forward + torch autograd + clip/Adam' % (nt, B, tsecs)}
+
+    fp16_on = bool(args.recurrent_fp16) and K.DEFAULT_BACKEND == 1
     line = {
         'metric': METRIC, 'value': value, 'unit': 'mixtures/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': ('f32 (tcgen05 products on bf16 hi/lo splits, fp32 accumulate' +
-                  ('; recurrent state enters its product as fp16)' if args.recurrent_fp16 else ')'))
+                  ('; recurrent state enters its product as fp16)' if fp16_on else ')'))
         if K.DEFAULT_BACKEND == 1 else 'f32',
-        'data': 'synthetic', 'config': workload_config(B, 'cuda', bool(args.recurrent_fp16) and K.DEFAULT_BACKEND == 1),
+        'data': 'synthetic', 'config': workload_config(B),
+        'where': 'cuda (one process per GPU%s)' % (', host buffers bound to NUMA node %s' % numa if numa is not None else ''),
+        'schedule': 'CUDA graph, 4 stream groups of 8 utterances, staggered',
+        'arithmetic': 'fp32 in / out; tensor-core products on bf16 hi/lo splits (3 products, fp32 accumulate)' +
+                      ('; the recurrent product takes h_{t-1} as one fp16 value x fp16 hi/lo weights' if fp16_on else ''),
+        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph),
+        'kernels': kernels, 'other_configs': other, 'precision_ab': precision_ab,
+        'clocks': clocks, 'gpu_launches': launches // args.steps, 'gpu_launches_timed_region': launches,
+        'cpu_baseline': cpu_baseline, 'roofline': roofline, 'parity': parity,
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
-        'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clocks,
-        'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph), 'train': train, 'kernels': kernels,
-        'parity': parity, 'other_configs': other,
+        # last on purpose: log tails keep the end of the line
+        'train': train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,6 +39,8 @@ class Model(object):
         self._last_split = None           # (hidden sequence, its split copy) handed from layer to layer
         self._tape = None                 # training: saved activations per recurrent layer
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
+        self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
+        self._ar_events = []
         self.step_count = 0
 
     # ---------------------------------------------------------------- variables
@@ -165,6 +167,14 @@ class Model(object):
     # pair: half the DSMEM bytes per step, ~1e-4 max-norm deviation of the embedding (tools/precision_study.py) against
     # the 1e-3 parity gate.  False = bf16x3 everywhere (~1e-5).  Training always uses bf16x3.
     RECURRENT_FP16 = True
+
+    def recurrent_backend(self):
+        """C-ABI backend of the inference recurrence: 2 (fp16 state) unless switched off -- or unless the inference
+        estimator makes hard assignments: k-means turns a 1e-4 embedding deviation into flipped cluster memberships
+        (measured at configs[3]: masks 1.6e-3 against the 1e-3 gate), so that plugin keeps bf16x3 throughout (2e-4)"""
+        if not self.RECURRENT_FP16 or getattr(self.infer_estimator, 'NEEDS_EXACT_EMBEDDING', False):
+            return 1
+        return 2
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
 
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
@@ -196,11 +206,11 @@ class Model(object):
             hp_stream.wait_stream(cur)
             with torch.cuda.stream(hp_stream):
                 out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
-                                            wh_packed=wh_packed, backend=2 if self.RECURRENT_FP16 else 1)
+                                            wh_packed=wh_packed, backend=self.recurrent_backend())
             cur.wait_stream(hp_stream)
         else:
             out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
-                                        wh_packed=wh_packed, backend=2 if self.RECURRENT_FP16 else 1)
+                                        wh_packed=wh_packed, backend=self.recurrent_backend())
         K.stamp('%s lstm' % name)
         self._last_split = (out, out_split)
         return out
@@ -258,10 +268,7 @@ class Model(object):
         gradient and Adam-moment buffers: the gradient all-reduce and the clip+Adam update are then one
         call each over ~9 M floats."""
         names = list(self.params)
-        offs, total = {}, 0
-        for k in names:
-            offs[k] = total
-            total += (self.params[k].numel() + 63) // 64 * 64          # 256-byte aligned views
+        offs, total = shard.flat_layout({k: self.params[k].numel() for k in names})   # 256-byte aligned views
         self._invalidate()
         flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         grad = torch.zeros_like(flat)
@@ -272,7 +279,17 @@ class Model(object):
             self.params[k] = view
         self._flat = dict(param=flat, grad=grad, m=torch.zeros_like(flat), v=torch.zeros_like(flat), offs=offs)
         self.grads = {k: grad[offs[k]:offs[k] + self.params[k].numel()].view(self.params[k].shape) for k in names}
+        self._buckets = shard.GradientBuckets(grad, {k: (offs[k], offs[k] + self.params[k].numel()) for k in names})
         return self._flat
+
+    BUCKETED_ALLREDUCE = True          # N > 1: all-reduce each layer's gradients as soon as they are queued (under BPTT)
+    TIME_ALLREDUCE = False             # bench: CUDA events around the part of the exchange the step has to wait for
+
+    def grads_ready(self, names):
+        """called by an encoder's backward on the stream that produced the gradients of `names`: their slice of the flat
+        buffer may be exchanged now (no-op on one rank)"""
+        if self.BUCKETED_ALLREDUCE and self._flat is not None:
+            self._buckets.reduce(names)
 
     def train_forward_backward(self, src):
         """One forward + backward of the train loss (main.py:289, 357-358) on complex spectra src [B,C,T,F];
@@ -315,13 +332,17 @@ class Model(object):
         return dict(loss=pit['loss'][0], snr=pit['snr'].mean(), perm_idx=pit['perm_idx'])
 
     def all_reduce_grads(self):
-        """the ONE collective of the system (SURVEY.md 8e): sum of the flat gradient buffer over ranks;
-        the mean is folded into the Adam kernel's grad_scale"""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self._flat['grad'])
-            return 1. / dist.get_world_size()
-        return 1.
+        """the ONE collective of the system: sum of the flat gradient buffer over ranks, bucketed per layer
+        in backward completion order (output projection + anchors, then L3 .. L0; shard.GradientBuckets) -- here only what
+        is still in flight is waited for and whatever no bucket covered is exchanged.  The 1/world mean is folded into the
+        clip + Adam kernel's grad_scale, i.e. the clip acts on the full-batch gradient (main.py:358-363)."""
+        if not self.TIME_ALLREDUCE:
+            return self._buckets.finish()
+        e0 = torch.cuda.current_stream().record_event(torch.cuda.Event(enable_timing=True))
+        scale = self._buckets.finish()
+        e1 = torch.cuda.current_stream().record_event(torch.cuda.Event(enable_timing=True))
+        self._ar_events.append((e0, e1))
+        return scale
 
     def apply_gradients(self, grad_scale=1.):
         """main.py:359-363: clip_by_value(+-GRAD_CLIP_THRES) then the registered optimiser (app/ozers.py), one fused

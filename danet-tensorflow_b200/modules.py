@@ -167,6 +167,8 @@ class _RecurrentEncoder(Encoder):
         side.wait_stream(main)
         with K.torch.cuda.stream(side):
             K.gemm(xc.view(B * T, odim), d_embed2, trans_a=True, out=g[self.name + '/output/W'])  # dW = X^T dY
+            # first bucket of the gradient exchange: the projection and (written before this backward) the anchors
+            model.grads_ready([self.name + '/output/W'] + [k for k in g if k.endswith('/anchors')])
         dx = K.center(dx.view(B, T, odim))             # the gradient of x - mean(x) is the same centring
         for l in range(len(tape) - 2, -1, -1):
             rec = tape[l]
@@ -202,6 +204,8 @@ class _RecurrentEncoder(Encoder):
                     b2 = K.split_operand(da_d, True)
                     K.gemm_split(a2, b2, I + H, 4 * H, T * B, out=dW)
                     K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
+                # this layer's gradients are queued: exchange them under the next layer's backward recurrence
+                model.grads_ready([n + sfx for n in names for sfx in ('/LSTM/linear/W', '/LSTM/linear/B')])
         main.wait_stream(side)
 
 
@@ -341,6 +345,7 @@ class KMeansEstimator(AnchoredEstimator):
     Lloyd iterations seeded with the anchor estimator's attractors."""
     USE_TRUTH = False
     N_ITER = 5
+    NEEDS_EXACT_EMBEDDING = True      # hard assignments: the model runs the recurrence in bf16x3 (Model.recurrent_backend)
 
     def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
         init = K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL)

@@ -233,7 +233,7 @@ def test_sgd_train_step_matches_oracle_autograd(D):
     """one whole training step with the `sgd` optimiser: parameters after the step against oracle forward +
     torch autograd + clip_sgd_step (OPTIMIZER_TYPE = 'sgd' is a registered choice, app/ozers.py:9-12)"""
     _configure(D, 1, False, BATCH_SIZE=2, TRAIN_ESTIMATOR_METHOD='truth-weighted', INFER_ESTIMATOR_METHOD='anchor',
-               SEPARATOR_TYPE='dot-sigmoid-orig', OPTIMIZER_TYPE='sgd', LR=1e-3)
+               SEPARATOR_TYPE='dot-sigmoid-orig', OPTIMIZER_TYPE='sgd', LR=100.)
     rs = np.random.RandomState(3)
     src_np = ((rs.standard_normal((2, 2, 24, 129)) + 1j * rs.standard_normal((2, 2, 24, 129))) * 5).astype(np.complex64)
     P = O.reference_init(1337, estimators=('infer_estimator',), dtype=torch.float64)
@@ -243,7 +243,7 @@ def test_sgd_train_step_matches_oracle_autograd(D):
     ref['train_loss'].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
     new = {k: v.detach().clone() for k, v in P.items()}
-    O.clip_sgd_step(new, grads, lr=1e-3, clip=100.)
+    O.clip_sgd_step(new, grads, lr=100., clip=100.)     # a rate at which the step is far above the fp32 spacing of the weights
     model = D.Model('sgd').build()
     model.load_params(P)
     out = model.train_step(torch.from_numpy(src_np).cuda())
@@ -252,3 +252,32 @@ def test_sgd_train_step_matches_oracle_autograd(D):
         step_ref = (new[k] - P[k]).numpy()
         step_got = model.params[k].detach().cpu().double().numpy() - P[k].numpy()
         assert np.abs(step_got - step_ref).max() <= 2e-3 * np.abs(step_ref).max() + 1e-9, k
+
+
+def test_sharded_product_gradients_equal_full_batch(D):
+    """SURVEY.md 8e on the CUDA path: the batch axis shards with no data-path collective, so the mean of the shards'
+    gradients (what the bucketed all-reduce + 1/world scale produce) equals the full-batch gradient, and one clip + Adam
+    step from either leaves the same parameters.  Two shards run back to back on this GPU (the 2-process NCCL run of the
+    same check is tests/test_gpu_multi.py)."""
+    _configure(D, 1, False, BATCH_SIZE=8)
+    K = D.kernels
+    g = torch.Generator(device='cuda').manual_seed(11)
+    src = K.stft(torch.randn(8, 2, 4000, device='cuda', generator=g) * 1000.)       # [8,2,64,129]
+    full = D.Model('full', seed=1337).build()
+    full.train_forward_backward(src)
+    gfull = full._flat['grad'].clone()
+    shard_grads = []
+    for r in range(2):
+        m = D.Model('shard%d' % r, seed=1337).build()
+        lo, hi = D.shard.shard_bounds(8, r, 2)
+        m.train_forward_backward(src[lo:hi].contiguous())
+        shard_grads.append(m._flat['grad'].clone())
+    mean = (shard_grads[0] + shard_grads[1]) * .5
+    scale = float(gfull.abs().max())
+    # bf16x3 products with different tilings of the batch: a few 1e-6 of the largest gradient entry
+    assert float((mean - gfull).abs().max()) < 5e-5 * scale, float((mean - gfull).abs().max()) / scale
+    # per variable, relative to that variable's own largest gradient entry
+    offs = full._flat['offs']
+    for k, v in full.params.items():
+        a, b = mean[offs[k]:offs[k] + v.numel()], gfull[offs[k]:offs[k] + v.numel()]
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12, k

@@ -377,6 +377,10 @@ def main():
         o = model.separator(None, attrs, flat, s_mixed_signals=mix, want=('sep', 'masks'))
         return embed.cpu().numpy(), o['masks'].cpu().numpy(), torch.view_as_real(o['sep']).cpu().numpy()
 
+    stages = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        stages = product_stages(min(args.cpu_baseline_mixtures, B, 8))     # before the training steps move the weights
+
     # ---- the training step of the same config (forward + backward + bucketed gradient all-reduce + clip/Adam)
     train = None
     if args.train_steps > 0:
@@ -528,7 +532,7 @@ def main():
         # the checker at work on the timed configuration: every tensor north_star names, product vs the fp32 CPU oracle
         # on the same mixtures (the fp64 comparison is tests/test_gpu_fullsize.py)
         npar = min(nb, 8)
-        g_embed, g_masks, g_sep = product_stages(npar)
+        g_embed, g_masks, g_sep = stages
         r_embed, r_masks = aux['embed'][:npar].numpy(), aux['masks'][:npar].numpy()
         r_sep = torch.view_as_real(aux['sig'][:npar]).numpy()
         got = got_e2e[:nb].numpy()

@@ -10,6 +10,7 @@ from .hparams import hparams, Hyperparameter
 from . import modules, datasets, ozers
 from .modules import Encoder, Estimator, Separator, ModelModule
 from .model import Model
+from .streaming import StreamingSeparator
 
 __all__ = ['hparams', 'Hyperparameter', 'kernels', 'modules', 'Model', 'Encoder', 'Estimator',
-           'Separator', 'ModelModule', 'build', '_lib']
+           'Separator', 'ModelModule', 'build', '_lib', 'StreamingSeparator']

@@ -9,6 +9,7 @@
 // float4 loads, phase 1 computes Wt for the tile (one thread per bin), phase 2 is a small
 // register-tiled product.  Partials go to the workspace; a finalize kernel reduces them in
 // a fixed order (deterministic, no atomics) and applies the estimator's epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace danet {
@@ -303,6 +304,225 @@ attractor_partial_kernel(const AttParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Anchor estimator, two sources, E = 20: the benchmark configuration (app/modules.py:501-545 with C = 2).
+// Same arithmetic as MODE_ANCHOR2 above (first-member sigmoids + an all-ones row), restructured around what the
+// round-1 profile showed (18 % of the HBM peak, 21 % warps active, three block barriers per 256-bin tile):
+//   * a WARP owns a chunk of 32 consecutive bins (2560 contiguous bytes) and never synchronises with another warp
+//     until the final reduction; the chunks arrive by cp.async.bulk into a per-warp double buffer, so the next
+//     chunk's HBM latency hides under the current chunk's arithmetic;
+//   * the weighted sums  acc[r][e] += S[bin][r] * V[bin][e]  (eq.7; 16 rows x 21 columns x 32 bins per chunk) are
+//     a small matrix product and run on the tensor cores: mma.sync m16n8k8 on TF32 hi/lo splits of BOTH operands,
+//     three products per term ("3xTF32": ~fp32 accuracy, far inside the 5e-5 the unit test asks for) -- 36 MMAs in
+//     place of 10 752 FMAs per chunk; column 20 of the B operand is the constant 1, so the weight sums (the
+//     denominators of eq.7) fall out of the same product;
+//   * the six anchor logits of a bin are computed once by the lane that owns the bin and shared through 1 KB of
+//     shared memory; every lane then evaluates the sigmoids of exactly the (row, bin) pairs its A fragment holds.
+// Deterministic: chunk -> warp assignment and every summation order are fixed.
+constexpr int kMmaE = 20;
+constexpr int kMmaChunk = 32;                       // bins per warp step = MMA K (4 x k8)
+constexpr int kMmaWarps = 8;
+constexpr int kMmaLd = kMmaE + 4;                   // partial row: 20 sums, weight sum, 3 zeros (= finalize's ld)
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}"
+      ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kMmaWarps)
+attractor_anchor2_mma_kernel(const float* __restrict__ embed, const float* __restrict__ anchors, float* __restrict__ part,
+                             long long TF, int n_anchor, int n_sub) {
+  extern __shared__ __align__(128) uint8_t mma_smem[];
+  typedef float VBuf[2][kMmaChunk * kMmaE];
+  typedef float LBuf[kMmaChunk][8];
+  VBuf* sV = reinterpret_cast<VBuf*>(mma_smem);                               // per-warp double buffer: [bin][e]
+  LBuf* sL = reinterpret_cast<LBuf*>(sV + kMmaWarps);                         // anchor logits of the chunk's bins
+  float* sA = reinterpret_cast<float*>(sL + kMmaWarps);                       // anchors [n_anchor][E]
+  typedef uint64_t Bars[2];
+  Bars* bars = reinterpret_cast<Bars*>(sA + kMaxAnchor * kMmaE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int gid = lane >> 2, tig = lane & 3;
+  const float* Vb = embed + (size_t)b * TF * kMmaE;
+
+  for (int i = tid; i < n_anchor * kMmaE; i += 32 * kMmaWarps) sA[i] = anchors[i];
+  if (lane == 0) {
+    uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&bars[warp][0]), a1 = (uint32_t)__cvta_generic_to_shared(&bars[warp][1]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // the rows of this lane's A fragments: r0 = gid, r1 = gid + 8; row r < n_sub is pair r in combinations order (a < b),
+  // row n_sub is the all-ones row, rows above are empty
+  int pa[2], pb[2], kind[2];                           // kind 0: pair, 1: ones, 2: empty
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = gid + 8 * h;
+    pa[h] = 0; pb[h] = 1;
+    kind[h] = r < n_sub ? 0 : (r == n_sub ? 1 : 2);
+    if (r < n_sub) {
+      int s = 0;
+      for (int a = 0; a < n_anchor; ++a)
+        for (int bq = a + 1; bq < n_anchor; ++bq, ++s)
+          if (s == r) { pa[h] = a; pb[h] = bq; }
+    }
+  }
+
+  // chunk c of the utterance goes to warp slot (c mod n_slots); a slot walks c, c + n_slots, ...
+  const long long n_chunks = (TF + kMmaChunk - 1) / kMmaChunk;
+  const long long n_slots = (long long)gridDim.x * kMmaWarps;
+  const long long slot = (long long)blk * kMmaWarps + warp;
+  float acc[3][4];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+
+  auto issue = [&](long long c, int buf) {
+    const long long bin0 = c * kMmaChunk;
+    const int n_here = (int)(TF - bin0 < kMmaChunk ? TF - bin0 : kMmaChunk);
+    const uint32_t bytes = (uint32_t)n_here * kMmaE * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(&bars[warp][buf])), "r"(bytes) : "memory");
+    bulk_g2s(&sV[warp][buf][0], Vb + (size_t)bin0 * kMmaE, bytes, &bars[warp][buf]);
+  };
+
+  if (slot < n_chunks && lane == 0) issue(slot, 0);
+  int it = 0;
+  for (long long c = slot; c < n_chunks; c += n_slots, ++it) {
+    const int buf = it & 1;
+    if (c + n_slots < n_chunks && lane == 0) issue(c + n_slots, buf ^ 1);     // that buffer was drained an iteration ago
+    mbar_wait_parity(&bars[warp][buf], (uint32_t)(it >> 1) & 1);
+    const long long bin0 = c * kMmaChunk;
+    const int n_here = (int)(TF - bin0 < kMmaChunk ? TF - bin0 : kMmaChunk);
+    const float* tile = &sV[warp][buf][0];
+
+    // ---- the six anchor logits of bin (bin0 + lane): 5 x LDS.128 of the bin's row (row stride 20 floats: conflict-free)
+    {
+      float lg[kMaxAnchor];
+#pragma unroll
+      for (int a = 0; a < kMaxAnchor; ++a) lg[a] = 0.f;
+      if (lane < n_here) {
+#pragma unroll
+        for (int e = 0; e < kMmaE; e += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(tile + lane * kMmaE + e);
+#pragma unroll
+          for (int a = 0; a < kMaxAnchor; ++a)
+            if (a < n_anchor) {
+              const float4 an = *reinterpret_cast<const float4*>(sA + a * kMmaE + e);
+              lg[a] = fmaf(x.x, an.x, lg[a]);
+              lg[a] = fmaf(x.y, an.y, lg[a]);
+              lg[a] = fmaf(x.z, an.z, lg[a]);
+              lg[a] = fmaf(x.w, an.w, lg[a]);
+            }
+        }
+      }
+      *reinterpret_cast<float4*>(&sL[warp][lane][0]) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+      *reinterpret_cast<float4*>(&sL[warp][lane][4]) = make_float4(lg[4], lg[5], lg[6], lg[7]);
+    }
+    __syncwarp();
+
+    // ---- acc[16 x 24] += S^T[16 x 32] * [V | 1 | 0][32 x 24], four k8 steps
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      // A fragment: a0 (row gid, bin tig), a1 (row gid+8, bin tig), a2 (row gid, bin tig+4), a3 (row gid+8, bin tig+4)
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 8 * ks + tig + 4 * j;
+        const bool ok = k < n_here;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float sv;
+          if (kind[h] == 0) {
+            // softmax over the pair (a, b): S_a = 1 / (1 + exp(l_b - l_a))   (eq.6 with C = 2)
+            const float d = sL[warp][k][pb[h]] - sL[warp][k][pa[h]];
+            sv = __fdividef(1.f, 1.f + __expf(d));
+          } else {
+            sv = kind[h] == 1 ? 1.f : 0.f;
+          }
+          if (!ok) sv = 0.f;
+          split_tf32(sv, ahi[2 * j + h], alo[2 * j + h]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        // B fragment: b0 (bin tig, column 8 nt + gid), b1 (bin tig + 4, same column); column 20 is the constant 1
+        const int n = 8 * nt + gid;
+        uint32_t bhi[2], blo[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = 8 * ks + tig + 4 * j;
+          float x = 0.f;
+          if (k < n_here) x = n < kMmaE ? tile[k * kMmaE + n] : (n == kMmaE ? 1.f : 0.f);
+          split_tf32(x, bhi[j], blo[j]);
+        }
+        mma_tf32(acc[nt], alo, bhi[0], bhi[1]);        // small terms first
+        mma_tf32(acc[nt], ahi, blo[0], blo[1]);
+        mma_tf32(acc[nt], ahi, bhi[0], bhi[1]);
+      }
+    }
+    __syncwarp();                                        // sL / this buffer are rewritten next iteration
+  }
+
+  // ---- fixed-order reduction of the eight warps' fragments, then one partial per block
+  // accumulator fragment: c0 (row gid, col 2 tig), c1 (row gid, col 2 tig + 1), c2 / c3 the same for row gid + 8
+  // (the fragments go through each warp's own, fully drained, chunk buffer: 16 x 24 floats of its 2 x 640)
+  float* red = &sV[warp][0][0];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) {
+    const int col = 8 * nt + 2 * tig;
+    red[gid * kMmaLd + col] = acc[nt][0];
+    red[gid * kMmaLd + col + 1] = acc[nt][1];
+    red[(gid + 8) * kMmaLd + col] = acc[nt][2];
+    red[(gid + 8) * kMmaLd + col + 1] = acc[nt][3];
+  }
+  __syncthreads();
+  float* dst = part + ((size_t)b * kParts + blk) * (size_t)(n_sub + 1) * kMmaLd;
+  for (int i = tid; i < (n_sub + 1) * kMmaLd; i += 32 * kMmaWarps) {
+    float sum = sV[0][0][i];
+#pragma unroll
+    for (int w = 1; w < kMmaWarps; ++w) sum += sV[w][0][i];
+    dst[i] = sum;
+  }
+}
+
+static int launch_anchor2_mma(const float* embed, const float* anchors, float* part, int B, long long TF, int n_anchor,
+                              int n_sub, cudaStream_t st) {
+  constexpr size_t smem = (size_t)kMmaWarps * (2 * kMmaChunk * kMmaE + kMmaChunk * 8) * 4 + kMaxAnchor * kMmaE * 4 +
+                          kMmaWarps * 2 * 8;
+  DANET_CUDA(cudaFuncSetAttribute(attractor_anchor2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attractor_anchor2_mma_kernel<<<dim3(kParts, B), 32 * kMmaWarps, smem, st>>>(embed, anchors, part, TF, n_anchor, n_sub);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
 // one block per utterance: sum the partials, then the estimator epilogue
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -511,7 +731,12 @@ extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* ancho
     }
   }
   const bool halved = C == 2 && (E == 4 || E == 12 || E == 20 || E == 40);   // fast path instantiations
-  if (halved) {
+  // tensor-core path for the benchmark configuration (two sources, E = 20, at most 15 pairs); DANET_ATTRACTOR_SIMT=1
+  // forces the register-tiled SIMT kernel (A/B runs, cross-check)
+  const bool mma = halved && E == kMmaE && P + 1 <= 16 && !getenv("DANET_ATTRACTOR_SIMT");
+  if (mma) {
+    rc = launch_anchor2_mma(embed, anchors, p.part, B, TF, n_anchor, P, as_stream(stream));
+  } else if (halved) {
     p.R = P + 1;
     rc = launch_partial<MODE_ANCHOR2>(p, B, n_anchor * E, as_stream(stream));
     p.R = P * C;

@@ -169,12 +169,8 @@ class Model(object):
     RECURRENT_FP16 = True
 
     def recurrent_backend(self):
-        """C-ABI backend of the inference recurrence: 2 (fp16 state) unless switched off -- or unless the inference
-        estimator makes hard assignments: k-means turns a 1e-4 embedding deviation into flipped cluster memberships
-        (measured at configs[3]: masks 1.6e-3 against the 1e-3 gate), so that plugin keeps bf16x3 throughout (2e-4)"""
-        if not self.RECURRENT_FP16 or getattr(self.infer_estimator, 'NEEDS_EXACT_EMBEDDING', False):
-            return 1
-        return 2
+        """C-ABI backend of the inference recurrence: 2 (fp16 state) unless switched off"""
+        return 2 if self.RECURRENT_FP16 else 1
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
 
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
@@ -485,6 +481,7 @@ class Model(object):
         self._packed_ready = True
 
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
+    PREFETCH_H2D = True     # pinned host input: the groups' slices are copied in order by one copy stream
     PIPELINE_MAX_GROUPS = 4
 
     def separate(self, wav, groups=None, out=None):
@@ -519,11 +516,12 @@ class Model(object):
         if out is None:
             out = torch.empty((B, Cn, K.FFT_STRIDE * T), dtype=torch.float32, device=self.device)
 
-        def run(lo, hi):
+        def run(lo, hi, w=None):
             K.stamp('g%d start' % lo)
-            w = wav[lo:hi]
-            if not w.is_cuda:
-                w = w.to(self.device, non_blocking=True)
+            if w is None:
+                w = wav[lo:hi]
+                if not w.is_cuda:
+                    w = w.to(self.device, non_blocking=True)
             mix, logmag = K.stft(w, want_logmag=True)
             K.stamp('g%d stft' % lo)
             fused = (self.USE_FUSED_K4 and getattr(self.separator, 'SUPPORTS_WAV', False) and Cn <= K.FUSED_K4_MAX_C
@@ -549,17 +547,32 @@ class Model(object):
         self._prepare_packed(hparams.FEATURE_SIZE)      # shared weight images: built before the fork, on one stream
         fork = main.record_event()
         streams = self._side_streams(groups)
+        staged = [None] * groups
+        if not wav.is_cuda and self.PREFETCH_H2D:
+            # host input: ONE copy stream moves the groups' slices in order, each at the full link rate, ahead of the
+            # staggered starts (a group that copies its own slice when it starts delays every later group by the copy
+            # time: measured +104 us on the last group's start; concurrent copies from four streams share the link and
+            # delay the FIRST group instead)
+            cp = self.side_stream('h2d')
+            cp.wait_event(fork)
+            with torch.cuda.stream(cp):
+                for g in range(groups):
+                    lo, hi = shard.shard_bounds(B, g, groups)
+                    w = wav[lo:hi].to(self.device, non_blocking=True)
+                    staged[g] = (w, cp.record_event())
         prev = None
         for g, st in enumerate(streams):
             lo, hi = shard.shard_bounds(B, g, groups)
             st.wait_event(fork)
+            if staged[g] is not None:
+                st.wait_event(staged[g][1])
             if prev is not None:
                 # stagger: group g starts once group g-1 has queued its first dense layer, so the groups
                 # do not march in lockstep (all dense, then all recurrent) but interleave the two phases
                 st.wait_event(prev)
             with torch.cuda.stream(st):
                 self._stagger_pending, self._stagger_event = True, None
-                run(lo, hi)
+                run(lo, hi, staged[g][0] if staged[g] is not None else None)
                 prev = self._stagger_event
                 self._stagger_pending = False
         for st in streams:

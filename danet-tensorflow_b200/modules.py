@@ -345,7 +345,6 @@ class KMeansEstimator(AnchoredEstimator):
     Lloyd iterations seeded with the anchor estimator's attractors."""
     USE_TRUTH = False
     N_ITER = 5
-    NEEDS_EXACT_EMBEDDING = True      # hard assignments: the model runs the recurrence in bf16x3 (Model.recurrent_backend)
 
     def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
         init = K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL)

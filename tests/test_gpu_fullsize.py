@@ -84,7 +84,8 @@ def _product_stages(D, model, wav):
     return dict(embed=embed, attrs=attrs, masks=out['masks'], sep=out['sep'])
 
 
-def _check_against_oracle(got, wavs, ref_wav, ref_sig, aux, n_ref, what):
+def _check_against_oracle(got, wavs, ref_wav, ref_sig, aux, n_ref, what, tol=None):
+    tol = tol or {}
     errs = dict(
         embed=rel(got['embed'][:n_ref], aux['embed']),
         attrs=rel(got['attrs'][:n_ref], aux['attrs']),
@@ -93,7 +94,7 @@ def _check_against_oracle(got, wavs, ref_wav, ref_sig, aux, n_ref, what):
         wav=rel(wavs[:n_ref], ref_wav))
     print('%s: max-norm errors vs the fp64 oracle: %s' % (what, ', '.join('%s %.2e' % kv for kv in errs.items())))
     for k, v in errs.items():
-        assert v < TOL, (what, k, v, errs)
+        assert v < tol.get(k, TOL), (what, k, v, errs)
     return errs
 
 
@@ -164,7 +165,17 @@ def test_cfg4_three_speakers_8s(D, est):
         _, _, sim, choice = O.estimator_anchor(aux['embed'], P['infer_estimator/anchors'], C, return_all=True)
         gchoice = D.kernels.attractor_anchor(got['embed'], model.params['train_estimator/anchors'], C, return_all=True)[3]
         assert np.array_equal(gchoice[:n_ref].cpu().numpy(), choice.numpy())
-    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, n_ref, 'cfg4 ' + est)
+    tol = None
+    if est == 'kmeans':
+        # Lloyd's hard assignments are discontinuous in the embedding: bins on a cluster boundary change sides under a
+        # 1e-5 perturbation (measured: embedding 1.2e-5 -> attractors 4e-4, masks 1.0e-3), whatever the arithmetic.  The
+        # estimator itself is therefore gated on the PRODUCT's embedding (same input -> same assignments, 1e-4), the whole
+        # path end to end at 3e-3; the embedding keeps the 1e-3 gate.  (New plugin, no reference twin: parity unpinned.)
+        V = got['embed'][:n_ref].double().cpu()
+        A_ref = O.estimator_kmeans(V, C, n_iter=5, init=O.estimator_anchor(V, P['infer_estimator/anchors'], C))
+        assert rel(got['attrs'][:n_ref], A_ref) < 1e-4
+        tol = dict(attrs=3e-3, masks=3e-3, spectra=3e-3, wav=3e-3)
+    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, n_ref, 'cfg4 ' + est, tol)
 
 
 def test_cfg5_30s_stream(D):
@@ -281,3 +292,42 @@ def test_sharded_product_gradients_equal_full_batch(D):
     for k, v in full.params.items():
         a, b = mean[offs[k]:offs[k] + v.numel()], gfull[offs[k]:offs[k] + v.numel()]
         assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12, k
+
+
+def test_streaming_front_and_back_end_cfg5(D):
+    """configs[4] fed as a stream: audio arrives in ragged chunks, every frame is transformed as soon as
+    its samples are in, the separated audio leaves in blocks.  Bit-identical to the batch call on the whole waveform."""
+    import bench
+    K = D.kernels
+    n = 240000
+    _configure(D, 1, True, BATCH_SIZE=1)
+    model = D.Model('stream').build()
+    wav_np = bench.synth_mixtures(1, n, 5)
+    wav = torch.from_numpy(wav_np).cuda()
+    ref = model.separate(wav)[0]
+    mix_ref, logmag_ref = K.stft(wav, want_logmag=True)
+    st = D.StreamingSeparator(model, max_seconds=31.)
+    rs = np.random.RandomState(0)
+    pos, done = 0, []
+    host = torch.from_numpy(wav_np[0]).pin_memory()
+    while pos < n:
+        m = int(min(n - pos, rs.choice([1, 63, 64, 100, 800, 4000, 16000])))
+        done.append(st.feed(host[pos:pos + m]))
+        pos += m
+    T = K.num_frames(n)
+    assert done[-1] >= T - 6 and all(a <= b for a, b in zip(done, done[1:]))      # the front end kept up with the audio
+    assert torch.equal(st.mix[:, :done[-1]], mix_ref[:, :done[-1]])
+    out, events = st.finish()
+    assert torch.equal(st.mix[:, :T], mix_ref) and torch.equal(st.logmag[:, :T], logmag_ref)
+    assert len(events) == -(-T // st.out_block)
+    events[0][1].synchronize()                                   # the first block alone is usable
+    assert torch.equal(out[:, :64 * st.out_block], ref[:, :64 * st.out_block].cpu())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref.cpu())
+    # a second stream through the same object (stale samples beyond the new end must not leak in)
+    st.reset()
+    st.feed(host[:5000])
+    st.feed(host[5000:12345])
+    out2, _ = st.finish()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, model.separate(wav[:, :12345])[0].cpu())

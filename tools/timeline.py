@@ -10,9 +10,13 @@ hp = D.hparams
 hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
              SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=32)); hp.digest()
 model = D.Model('t', 'cuda:0').build()
-wav = torch.from_numpy(bench.synth_mixtures(32, 32000, 1)).cuda()
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 32000          # samples per utterance (T = N/64 + 1 frames)
+HOST = len(sys.argv) > 2 and sys.argv[2] == 'host'             # pinned host buffers in and out (the e2e call)
+wav = torch.from_numpy(bench.synth_mixtures(32, N, 1))
+wav = wav.pin_memory() if HOST else wav.cuda()
+out_host = torch.empty((32, 2, 64 * K.num_frames(N)), dtype=torch.float32).pin_memory() if HOST else None
 for _ in range(2):
-    model.separate(wav)
+    model.separate(wav, out=out_host)
 buf = torch.zeros(4096, dtype=torch.int64, device='cuda')
 labels = []
 K._timeline = (buf, labels)
@@ -20,7 +24,7 @@ graph = torch.cuda.CUDAGraph()
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
     with torch.cuda.graph(graph, stream=side):
-        y = model.separate(wav)
+        y = model.separate(wav, out=out_host)
 K._timeline = None
 for _ in range(3):
     graph.replay()
@@ -42,4 +46,4 @@ for g in order:
     for lab, ts in rows[g]:
         print('  %-28s at %8.1f us  (+%7.1f)' % (lab, ts, ts - prev if prev is not None else 0.))
         prev = ts
-print('total %.1f us' % ((t.max() - t0) / 1e3))
+print('N = %d samples, %s: total %.1f us' % (N, 'pinned host in/out' if HOST else 'device resident', (t.max() - t0) / 1e3))

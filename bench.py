@@ -298,7 +298,7 @@ def main():
             return r
         setattr(K, name, timed)
     for nm in ('lstm_seq', 'lstm_seq_bwd', 'stft', 'istft', 'attractor_anchor', 'mask_cmul', 'mask_cmul_istft', 'gemm_split',
-               'split_operand', 'mean'):
+               'proj_anchor', 'split_operand', 'mean'):
         instrument(nm)
 
     def barrier():
@@ -502,7 +502,11 @@ def main():
             ('istft', 'hbm', B * N_SPK * (8. * TF + 4. * 64 * T), 'spectra in, waveforms out'),
             ('mask_cmul_istft', 'hbm', B * (4. * TF * E + 8. * TF + 4. * N_SPK * 64 * T),
              'K4 fused: embedding + mixture in, separated waveforms out (masked spectra stay in shared memory)'),
-            ('gemm_split', 'tensor', None, 'hoisted input projections (N = 2400) and the output projection (N = 2580), bf16x3')):
+            ('proj_anchor', 'tensor', 2. * B * T * 600 * 2580,
+             'output projection (N = 2580) with the anchor estimator\'s sums in its epilogue (replaces gemm + attractor_anchor); '
+             'also streams 4*T*F*E bytes of embedding out'),
+            ('gemm_split', 'tensor', None, 'hoisted input projections (N = 2400)' +
+             ('' if per_kernel.get('proj_anchor') else ' and the output projection (N = 2580)') + ', bf16x3')):
         ms = avg_ms(name)
         if ms is None:
             continue
@@ -510,9 +514,14 @@ def main():
             ach = work / (ms * 1e-3) / 1e9
             kernels.append({'kernel': name, 'bound': 'hbm', 'ms_per_launch': ms, 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
                             'frac': ach / hbm, 'note': note})
+        elif work is not None:
+            ach = work / (ms * 1e-3) / 1e12
+            kernels.append({'kernel': name, 'bound': 'tensor', 'ms_per_launch': ms, 'achieved': ach, 'issued': 3 * ach,
+                            'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'frac_issued': 3 * ach / peak_tf,
+                            'note': note})
         else:
             n_calls = len(per_kernel[name]) // args.steps
-            gflops = 2. * B * T * (129 * 2400 + 3 * 600 * 2400 + 600 * 2580)          # logical fp32 flops per step
+            gflops = 2. * B * T * (129 * 2400 + 3 * 600 * 2400 + (0 if per_kernel.get('proj_anchor') else 600 * 2580))
             tot_ms = ms * n_calls
             ach = gflops / (tot_ms * 1e-3) / 1e12
             kernels.append({'kernel': name, 'bound': 'tensor', 'ms_per_step': tot_ms, 'launches_per_step': n_calls,

@@ -44,6 +44,9 @@ PROTOTYPES = {
     'danet_split_operand': (c_i, [c_f, c_ll, c_i, c_i, c_i, c_v, c_i, c_i, c_v]),
     'danet_split_operand_paired': (c_i, [c_f, c_ll, c_i, c_i, c_i, c_i, c_v, c_i, c_i, c_v]),
     'danet_gemm_split': (c_i, [c_v, c_v, c_f, c_f, c_f, c_i, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_v]),
+    'danet_proj_anchor_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
+    'danet_proj_anchor_fwd': (c_i, [c_v, c_v, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_v, c_i, c_i, c_i, c_i, c_i, c_i,
+                                    c_v, c_sz, c_v]),
     'danet_mean_fwd': (c_i, [c_f, c_i, c_ll, c_f, c_f, c_v]),
     'danet_lstm_seq_bwd_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
     'danet_lstm_seq_bwd': (c_i, [c_f, c_f, c_f, C.POINTER(C.c_void_p), c_ll, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),

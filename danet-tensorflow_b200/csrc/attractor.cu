@@ -11,6 +11,7 @@
 // a fixed order (deterministic, no atomics) and applies the estimator's epilogue.
 #include <stdlib.h>
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace danet {
 
@@ -325,20 +326,6 @@ constexpr int kMmaChunk = 32;                       // bins per warp step = MMA 
 constexpr int kMmaWarps = 8;
 constexpr int kMmaLd = kMmaE + 4;                   // partial row: 20 sums, weight sum, 3 zeros (= finalize's ld)
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
@@ -529,7 +516,7 @@ __global__ void __launch_bounds__(256)
 attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, int nQ, int n_sub,
                           float denom_add, float* __restrict__ attractors,
                           float* __restrict__ attractor_sets, float* __restrict__ sims,
-                          int* __restrict__ choice, float* __restrict__ den_out, int halved) {
+                          int* __restrict__ choice, float* __restrict__ den_out, int halved, int n_parts) {
   __shared__ float s_sum[kAttMaxRows * (kAttMaxE + 4)];
   __shared__ float s_sim[32];
   __shared__ int s_choice;
@@ -541,8 +528,8 @@ attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, i
     for (int i = tid; i < n_sub * ld; i += 256) {
       const int s = i / ld, e = i % ld;
       float first = 0.f, total = 0.f;
-      for (int pt = 0; pt < kParts; ++pt) {
-        const float* pp = part + ((size_t)b * kParts + pt) * np;
+      for (int pt = 0; pt < n_parts; ++pt) {
+        const float* pp = part + ((size_t)b * n_parts + pt) * np;
         first += pp[s * ld + e];
         total += pp[n_sub * ld + e];
       }
@@ -552,7 +539,7 @@ attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, i
   } else {
     for (int i = tid; i < n; i += 256) {
       float s = 0.f;
-      for (int pt = 0; pt < kParts; ++pt) s += part[((size_t)b * kParts + pt) * n + i];
+      for (int pt = 0; pt < n_parts; ++pt) s += part[((size_t)b * n_parts + pt) * n + i];
       s_sum[i] = s;
     }
   }
@@ -654,6 +641,18 @@ static int launch_partial(AttParams& p, int B, int n_aux, cudaStream_t st) {
   return DANET_OK;
 }
 
+// eq.7 normalisation, eq.8 similarity, eq.9 selection on partial sums produced elsewhere (the fused output projection,
+// gemm_tc.cu): `n_parts` partials of [(n_sub + 1)][E + 4] per utterance in the halved two-source layout
+int attractor_anchor_finalize(const float* part, int n_parts, int B, int E, int n_sub, float* attractors, float* sets,
+                              float* sims, int* choice, float* den, cudaStream_t stream) {
+  DANET_REQUIRE(E % 4 == 0 && E <= kAttMaxE && 2 * n_sub <= kAttMaxRows && n_sub <= 20, DANET_E_SHAPE,
+                "attractor finalize: E %d n_sub %d", E, n_sub);
+  attractor_finalize_kernel<MODE_ANCHOR><<<B, 256, 0, stream>>>(part, 2, E, 2 * n_sub, E / 4 + 1, n_sub, 0.f, attractors, sets,
+                                                                sims, choice, den, 1, n_parts);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
 static int check_common(const char* who, const float* embed, int B, int C, int TF, int E, int R,
                         void* ws, size_t ws_bytes) {
   DANET_REQUIRE(embed && ws, DANET_E_ARG, "%s: null pointer", who);
@@ -697,7 +696,7 @@ extern "C" int danet_attractor_truth_fwd(const float* embed, const float* src_pw
   rc = launch_partial<MODE_TRUTH>(p, B, 0, as_stream(stream));
   if (rc) return rc;
   attractor_finalize_kernel<MODE_TRUTH><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr, den, 0);
+      p.part, C, E, p.R, p.nQ, 0, mode == 0 ? 1.f : kEps, attractors, nullptr, nullptr, nullptr, den, 0, kParts);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
@@ -745,7 +744,7 @@ extern "C" int danet_attractor_anchor_fwd(const float* embed, const float* ancho
   }
   if (rc) return rc;
   attractor_finalize_kernel<MODE_ANCHOR><<<B, 256, 0, as_stream(stream)>>>(
-      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice, den, halved ? 1 : 0);
+      p.part, C, E, p.R, p.nQ, P, 0.f, attractors, attractor_sets, similarities, choice, den, halved ? 1 : 0, kParts);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }
@@ -765,7 +764,7 @@ extern "C" int danet_attractor_kmeans_fwd(const float* embed, float* centroids, 
     rc = launch_partial<MODE_KMEANS>(p, B, C * E, as_stream(stream));
     if (rc) return rc;
     attractor_finalize_kernel<MODE_KMEANS><<<B, 256, 0, as_stream(stream)>>>(
-        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr, nullptr, 0);
+        p.part, C, E, p.R, p.nQ, 0, 0.f, centroids, nullptr, nullptr, nullptr, nullptr, 0, kParts);
     DANET_LAUNCH_CHECK();
   }
   return DANET_OK;

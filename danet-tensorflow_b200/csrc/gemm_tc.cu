@@ -13,6 +13,7 @@
 #include <atomic>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "mma_sync.cuh"
 
 namespace danet {
 
@@ -325,6 +326,333 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, 2 * kTN);
 }
 
+
+// ================================================================================================================
+// Output projection FUSED with the anchor estimator's accumulation:
+//   V[b,t,f,:] = (x[b,t,:] - mean_b) W[:, f E .. f E + E)          app/modules.py:244-259
+//   S[b,p,t,f] = softmax over the anchor pair p of <V[b,t,f], anchor>     :513-519 (eq.6, two sources)
+//   sum_{t,f} S V  and  sum_{t,f} S  per utterance and pair               :520-523 (eq.7's numerator / denominator)
+// in ONE kernel: the embedding tile never has to be read back for the estimator -- it is still in the epilogue warp's
+// registers / shared memory when the weighted sums are taken.  Same tcgen05 pipeline as gemm_bf16x3_kernel with
+//   * tiles of 128 rows x 160 columns: 160 = 8 whole time-frequency bins of E = 20, so a tile holds complete embedding
+//     vectors (UMMA N = 160; two 160-column accumulators in tensor memory);
+//   * row tiles cut per utterance (tile (b, mt) = frames 128 mt .. of utterance b; rows beyond T masked), so a tile's
+//     partial sums belong to one utterance;
+//   * eight epilogue warps: warp (q, hh) owns TMEM lanes 32 q .. and bins 4 hh .. 4 hh + 3 of the tile, two bins at a time:
+//     tcgen05.ld -> centring term -> the warp's 32 x 40 shared-memory tile -> (a) coalesced store of V, (b) six anchor
+//     logits per (row, bin), (c) the weighted sums on the tensor cores (mma.sync 3xTF32, as attractor_anchor2_mma_kernel:
+//     A = pair sigmoids evaluated in fragment layout, B = the tile with a constant-1 column for the denominators);
+//   * per tile a fixed-order reduction of the eight warps' fragments and ONE partial [16][24] written to
+//     part[b][mt][tx] -- indexed by tile, not by CTA, so the result does not depend on which CTA ran which tile
+//     (the tile scheduler is cluster launch control, i.e. dynamic); attractor_finalize sums the partials in order.
+constexpr int kPN = 160;
+constexpr int kPStages = 2;
+constexpr int kPTileA = kTM * kTK * 2;                        // 16 KB
+constexpr int kPTileB = kPN * kTK * 2;                        // 20 KB
+constexpr int kPStageBytes = 2 * kPTileA + 2 * kPTileB;       // 72 KB: A_hi, A_lo, B_hi, B_lo
+constexpr int kPE = 20;
+constexpr int kPPair = 2 * kPE;                               // columns handled at once: 2 bins
+constexpr int kPEpiWarps = 8;
+constexpr int kPThreads = 128 + 32 * kPEpiWarps;
+constexpr int kPLdL = 24;                                     // floats per row of the logit tile ([2 bins][8], padded)
+constexpr int kPWarpTile = 32 * kPPair * 4;                   // 5 KB
+constexpr int kPWarpL = 32 * kPLdL * 4;                       // 3 KB
+constexpr int kPRows = 16, kPLd = kPE + 4;                    // partial: 16 rows x 24
+constexpr int kPSmem = kPStages * kPStageBytes + 1024 + 512 + kPEpiWarps * (kPWarpTile + kPWarpL) + 8 * kPE * 4;
+
+struct ProjAnchorParams {
+  float* V;                 // [B*T][N]
+  const float* row_mu;      // [B] mean of x over (T, K), or null
+  const float* col_s;       // [N] column sums of W (with row_mu)
+  const float* anchors;     // [n_anchor][E]
+  float* part;              // [B][mtiles][ntiles][(n_sub+1)][24]
+  int B, T, N, F, M, n_kblocks, n_anchor, n_sub, mtiles, ntiles;
+};
+
+__global__ void __launch_bounds__(kPThreads, 1)
+proj_anchor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const ProjAnchorParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes);
+  uint64_t* empty_bar = full_bar + kPStages;
+  uint64_t* tmem_full_bar = empty_bar + kPStages;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint64_t* clc_full_bar = tmem_empty_bar + 2;          // [kClcSlots]
+  uint64_t* clc_empty_bar = clc_full_bar + kClcSlots;   // [kClcSlots]
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(clc_empty_bar + kClcSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_resp + 16 * kClcSlots);
+  uint8_t* epi = smem + kPStages * kPStageBytes + 512;
+  float* sA = reinterpret_cast<float*>(epi + kPEpiWarps * (kPWarpTile + kPWarpL));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + s, 1);
+      mbar_init(tmem_empty_bar + s, kPEpiWarps);
+    }
+    for (int s = 0; s < kClcSlots; ++s) {
+      mbar_init(clc_full_bar + s, 1);
+      mbar_init(clc_empty_bar + s, 1 + kPEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.n_anchor * kPE; i += kPThreads) sA[i] = p.anchors[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int tx = blockIdx.x, ty = blockIdx.y, tz = 0;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {   // ===== TMA producer + tile scheduler =====
+      uint32_t kbc = 0;
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+        mbar_wait(clc_empty_bar + slot, cph ^ 1);
+        mbar_arrive_expect_tx(clc_full_bar + slot, 16);
+        clc_try_cancel(smem_u32(clc_resp + 16 * slot), smem_u32(clc_full_bar + slot));
+        const int b = ty / p.mtiles, mt = ty % p.mtiles;
+        const int m0 = b * p.T + mt * kTM, n0 = tx * kPN;
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++kbc) {
+          const int s = kbc % kPStages;
+          const uint32_t ph = (kbc / kPStages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          uint8_t* st = smem + s * kPStageBytes;
+          mbar_arrive_expect_tx(full_bar + s, kPStageBytes);
+          const int kc = kb * kTK;
+          tma_load_2d(st, &map_a, full_bar + s, kc, m0);                                  // x hi
+          tma_load_2d(st + kPTileA, &map_a, full_bar + s, kc, p.M + m0);                  // x lo
+          tma_load_2d(st + 2 * kPTileA, &map_b, full_bar + s, kc, n0);                    // W^T hi
+          tma_load_2d(st + 2 * kPTileA + kPTileB, &map_b, full_bar + s, kc, p.N + n0);    // W^T lo
+        }
+        mbar_wait(clc_full_bar + slot, cph);
+        const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+        fence_proxy_async_smem();
+        if (!more) break;
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {   // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(kTM, kPN);
+      uint32_t kbc = 0;
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        const uint32_t tmem_acc = tmem_base + acc * kPN;
+        mbar_wait(tmem_empty_bar + acc, aph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++kbc) {
+          const int s = kbc % kPStages;
+          const uint32_t ph = (kbc / kPStages) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * kPStageBytes);
+          const uint64_t a_hi = umma_desc_k_sw128(base), a_lo = umma_desc_k_sw128(base + kPTileA);
+          const uint64_t b_hi = umma_desc_k_sw128(base + 2 * kPTileA), b_lo = umma_desc_k_sw128(base + 2 * kPTileA + kPTileB);
+#pragma unroll
+          for (int k = 0; k < kTK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            umma_bf16(tmem_acc, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_bf16(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tmem_full_bar + acc);
+        const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+        mbar_wait(clc_full_bar + slot, cph);
+        const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+        fence_proxy_async_smem();
+        mbar_arrive(clc_empty_bar + slot);
+        if (!more) break;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp (q, hh): TMEM lanes 32 q .. 32 q + 31 = rows, columns 80 hh .. 80 hh + 79 = bins 4 hh .. 4 hh + 3 =====
+    const int w = warp - 4, q = w & 3, hh = w >> 2;
+    const int gid = lane >> 2, tig = lane & 3;
+    float* tile = reinterpret_cast<float*>(epi + (size_t)w * (kPWarpTile + kPWarpL));     // [32][40]
+    float* sL = tile + 32 * kPPair;                                                       // [32][24]: logits [bin][8]
+    // rows of this lane's A fragments (see attractor_anchor2_mma_kernel): pair index -> (first, second) anchor
+    int pa[2], pb[2], kind[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = gid + 8 * h;
+      pa[h] = 0; pb[h] = 1;
+      kind[h] = r < p.n_sub ? 0 : (r == p.n_sub ? 1 : 2);
+      if (r < p.n_sub) {
+        int s = 0;
+        for (int a = 0; a < p.n_anchor; ++a)
+          for (int bq = a + 1; bq < p.n_anchor; ++bq, ++s)
+            if (s == r) { pa[h] = a; pb[h] = bq; }
+      }
+    }
+    const int part_ld = (p.n_sub + 1) * kPLd;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t acc_i = it & 1, aph = (it >> 1) & 1;
+      const uint32_t tmem_acc = tmem_base + acc_i * kPN;
+      const int b = ty / p.mtiles, mt = ty % p.mtiles;
+      const int n0 = tx * kPN;
+      const int t0 = mt * kTM + 32 * q;                       // first frame of this warp's rows
+      const int n_here = min(32, max(0, p.T - t0));           // valid rows form a prefix
+      const size_t g0 = (size_t)b * p.T + t0;                 // global row of the warp's row 0
+      const float mu = p.row_mu ? __ldg(p.row_mu + b) : 0.f;
+      float acc[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+      mbar_wait(tmem_full_bar + acc_i, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pp = 0; pp < 2; ++pp) {
+        const int c0 = 80 * hh + kPPair * pp;
+        const int bin0 = (n0 + c0) / kPE;
+        if (bin0 >= p.F) break;                               // warp-uniform: nothing left in this tile for the warp
+        const int nbin = min(2, p.F - bin0);
+        float v[kPPair];
+        {
+          float v32[32], v8[8];
+          tmem_ld_32x32(tmem_acc + ((uint32_t)(32 * q) << 16) + c0, v32);
+          tmem_ld_32x8(tmem_acc + ((uint32_t)(32 * q) << 16) + c0 + 32, v8);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v32[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[32 + j] = v8[j];
+        }
+        if (p.row_mu) {
+#pragma unroll
+          for (int j = 0; j < kPPair; j += 4) {
+            if (n0 + c0 + j < p.N) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.col_s + n0 + c0 + j));
+              v[j] = fmaf(-mu, cs.x, v[j]); v[j + 1] = fmaf(-mu, cs.y, v[j + 1]);
+              v[j + 2] = fmaf(-mu, cs.z, v[j + 2]); v[j + 3] = fmaf(-mu, cs.w, v[j + 3]);
+            }
+          }
+        }
+        __syncwarp();                                         // the previous pair's readers are done with tile / sL
+#pragma unroll
+        for (int j = 0; j < kPPair; j += 4)
+          *reinterpret_cast<float4*>(tile + lane * kPPair + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        // six anchor logits per (row, bin)
+#pragma unroll
+        for (int bs = 0; bs < 2; ++bs) {
+          float lg[8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) lg[a] = 0.f;
+#pragma unroll
+          for (int e = 0; e < kPE; e += 4) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              if (a < p.n_anchor) {
+                const float4 an = *reinterpret_cast<const float4*>(sA + a * kPE + e);
+                lg[a] = fmaf(v[kPE * bs + e], an.x, lg[a]);
+                lg[a] = fmaf(v[kPE * bs + e + 1], an.y, lg[a]);
+                lg[a] = fmaf(v[kPE * bs + e + 2], an.z, lg[a]);
+                lg[a] = fmaf(v[kPE * bs + e + 3], an.w, lg[a]);
+              }
+          }
+          *reinterpret_cast<float4*>(sL + lane * kPLdL + 8 * bs) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+          *reinterpret_cast<float4*>(sL + lane * kPLdL + 8 * bs + 4) = make_float4(lg[4], lg[5], lg[6], lg[7]);
+        }
+        __syncwarp();
+        // (a) the embedding leaves as whole 160-byte row segments (10 lanes per row)
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int idx = i * 32 + lane, r = idx / 10, part4 = idx - r * 10;
+          if (r < n_here && n0 + c0 + 4 * part4 < p.N)
+            *reinterpret_cast<float4*>(p.V + (g0 + r) * (size_t)p.N + n0 + c0 + 4 * part4) =
+                *reinterpret_cast<const float4*>(tile + r * kPPair + 4 * part4);
+        }
+        // (b) acc[16 x 24] += S^T[16 x 32 rows] * [V_bin | 1 | 0][32 rows x 24] for each bin of the pair
+        for (int bs = 0; bs < nbin; ++bs) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = 8 * ks + tig + 4 * j;
+              const bool ok = k < n_here;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float sv;
+                if (kind[h] == 0) {
+                  const float d = sL[k * kPLdL + 8 * bs + pb[h]] - sL[k * kPLdL + 8 * bs + pa[h]];
+                  sv = __fdividef(1.f, 1.f + __expf(d));
+                } else {
+                  sv = kind[h] == 1 ? 1.f : 0.f;
+                }
+                if (!ok) sv = 0.f;
+                split_tf32(sv, ahi[2 * j + h], alo[2 * j + h]);
+              }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+              const int n = 8 * nt + gid;
+              uint32_t bhi[2], blo[2];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int k = 8 * ks + tig + 4 * j;
+                float x = 0.f;
+                if (k < n_here) x = n < kPE ? tile[k * kPPair + kPE * bs + n] : (n == kPE ? 1.f : 0.f);
+                split_tf32(x, bhi[j], blo[j]);
+              }
+              mma_tf32(acc[nt], alo, bhi[0], bhi[1]);
+              mma_tf32(acc[nt], ahi, blo[0], blo[1]);
+              mma_tf32(acc[nt], ahi, bhi[0], bhi[1]);
+            }
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp before the (TMEM-free) reduction
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + acc_i);
+      // fixed-order reduction of the eight warps' fragments -> one partial per tile
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int col = 8 * nt + 2 * tig;
+        tile[gid * kPLd + col] = acc[nt][0];
+        tile[gid * kPLd + col + 1] = acc[nt][1];
+        tile[(gid + 8) * kPLd + col] = acc[nt][2];
+        tile[(gid + 8) * kPLd + col + 1] = acc[nt][3];
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kPEpiWarps) : "memory");
+      {
+        float* dst = p.part + (((size_t)b * p.mtiles + mt) * p.ntiles + tx) * part_ld;
+        for (int i = threadIdx.x - 128; i < part_ld; i += 32 * kPEpiWarps) {
+          float sum = 0.f;
+#pragma unroll
+          for (int ww = 0; ww < kPEpiWarps; ++ww)
+            sum += reinterpret_cast<const float*>(epi + (size_t)ww * (kPWarpTile + kPWarpL))[i];
+          dst[i] = sum;
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kPEpiWarps) : "memory");
+      const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
+      mbar_wait(clc_full_bar + slot, cph);
+      const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(clc_empty_bar + slot);
+      if (!more) break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- host -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -463,6 +791,60 @@ int linear_tc_fwd(const float* A, long long lda, const float* W, long long ldw, 
   GemmOperand a = {A, lda, 0, 0, 0}, b = {W, ldw, 0, 0, 0};
   return gemm_tc(a, b, bias, C, N, M, N, K, time_major_T, 0, workspace, workspace_bytes, stream);
 }
+
+int attractor_anchor_finalize(const float* part, int n_parts, int B, int E, int n_sub, float* attractors, float* sets,
+                              float* sims, int* choice, float* den, cudaStream_t stream);
+
+static inline int proj_anchor_mtiles(int T) { return (T + kTM - 1) / kTM; }
+static inline int proj_anchor_ntiles(int N) { return (N + kPN - 1) / kPN; }
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" size_t danet_proj_anchor_workspace_bytes(int B, int T, int F, int E) {
+  if (B < 1 || T < 1 || F < 1 || E < 1) return 256;
+  return (size_t)B * proj_anchor_mtiles(T) * proj_anchor_ntiles(F * E) * kPRows * kPLd * sizeof(float);
+}
+
+extern "C" int danet_proj_anchor_fwd(const void* A2, const void* W2, const float* row_mu, const float* col_s,
+                                     const float* anchors, float* embed, float* attractors, float* attractor_sets,
+                                     float* similarities, int* choice, int B, int T, int F, int E, int K, int n_anchor,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  DANET_REQUIRE(A2 && W2 && anchors && embed && attractors && workspace, DANET_E_ARG, "proj_anchor: null pointer");
+  DANET_REQUIRE(E == kPE, DANET_E_SHAPE, "proj_anchor: the fused kernel is built for E = %d (got %d); use danet_gemm_split + "
+                "danet_attractor_anchor_fwd", kPE, E);
+  DANET_REQUIRE(B >= 0 && T >= 1 && F >= 1 && K >= 1, DANET_E_SHAPE, "proj_anchor: B %d T %d F %d K %d", B, T, F, K);
+  const int n_sub = n_anchor * (n_anchor - 1) / 2;
+  DANET_REQUIRE(n_anchor >= 2 && n_anchor <= 6 && n_sub + 1 <= kPRows, DANET_E_SHAPE,
+                "proj_anchor: n_anchor %d (two sources, 2 .. 6 anchors)", n_anchor);
+  DANET_REQUIRE(!row_mu || (col_s && aligned16(col_s)), DANET_E_ARG, "proj_anchor: row_mu needs col_s (16-byte aligned)");
+  DANET_REQUIRE(aligned16(A2) && aligned16(W2) && aligned16(embed) && aligned16(workspace), DANET_E_ALIGN,
+                "proj_anchor: operands, embed and workspace must be 16-byte aligned");
+  DANET_REQUIRE(workspace_bytes >= danet_proj_anchor_workspace_bytes(B, T, F, E), DANET_E_WORKSPACE,
+                "proj_anchor: workspace %zu < %zu", workspace_bytes, danet_proj_anchor_workspace_bytes(B, T, F, E));
+  if (B == 0) return DANET_OK;
+  const int M = B * T, N = F * E, Kp = pad_k(K);
+  CUtensorMap map_a, map_b;
+  int rc = make_tensor_map_bf16(&map_a, A2, 2ll * M, Kp, kTM);
+  if (rc) return rc;
+  rc = make_tensor_map_bf16(&map_b, W2, 2ll * N, Kp, kPN);
+  if (rc) return rc;
+  ProjAnchorParams p;
+  p.V = embed; p.row_mu = row_mu; p.col_s = col_s; p.anchors = anchors;
+  p.part = reinterpret_cast<float*>(workspace);
+  p.B = B; p.T = T; p.N = N; p.F = F; p.M = M; p.n_kblocks = Kp / kTK; p.n_anchor = n_anchor; p.n_sub = n_sub;
+  p.mtiles = proj_anchor_mtiles(T); p.ntiles = proj_anchor_ntiles(N);
+  DANET_REQUIRE((long long)B * p.mtiles <= 65535, DANET_E_SHAPE, "proj_anchor: B %d x %d row tiles exceeds the grid", B, p.mtiles);
+  DANET_CUDA(cudaFuncSetAttribute(proj_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+  dim3 grid(p.ntiles, B * p.mtiles);
+  proj_anchor_kernel<<<grid, kPThreads, kPSmem, as_stream(stream)>>>(map_a, map_b, p);
+  DANET_LAUNCH_CHECK();
+  return attractor_anchor_finalize(p.part, p.mtiles * p.ntiles, B, E, n_sub, attractors, attractor_sets, similarities,
+                                   choice, nullptr, as_stream(stream));
+}
+
+namespace danet {
 
 }  // namespace danet
 

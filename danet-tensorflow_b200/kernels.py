@@ -348,6 +348,35 @@ def gemm_split(a2, b2, m, n, k, bias=None, out=None, out_perm_T=0, accumulate=Fa
     return out
 
 
+PROJ_ANCHOR_E = 20
+
+
+def proj_anchor(a2, w2, B, T, F, E, k, anchors, row_mu=None, col_s=None, return_all=False):
+    """
+    Output projection with the anchor estimator's sums taken in its epilogue [app/modules.py:244-259 + 501-545, two
+    sources]: split operands a2 [2*B*T, Kp], w2 [2*F*E, Kp] -> (embed [B,T,F,E], attractors [B,2,E]
+    (+ sets [B,P,2,E], sims [B,P], choice [B] int32)).  E = 20 and at most 6 anchors; otherwise ValueError.
+    """
+    anchors = _req(anchors, 'anchors', dim=2)
+    A = anchors.shape[0]
+    if anchors.shape[1] != E:
+        raise ValueError('proj_anchor: anchors %s, E = %d' % (tuple(anchors.shape), E))
+    dev = a2.device
+    P = A * (A - 1) // 2
+    embed = torch.empty((B, T, F, E), dtype=torch.float32, device=dev)
+    attrs = torch.empty((B, 2, E), dtype=torch.float32, device=dev)
+    sets = torch.empty((B, P, 2, E), dtype=torch.float32, device=dev) if return_all else None
+    sims = torch.empty((B, P), dtype=torch.float32, device=dev) if return_all else None
+    choice = torch.empty((B,), dtype=torch.int32, device=dev) if return_all else None
+    lib = _lib.load()
+    ws = _ws(lib.danet_proj_anchor_workspace_bytes(B, T, F, E), dev)
+    _lib.check(lib.danet_proj_anchor_fwd(_p(a2), _p(w2), _p(row_mu), _p(col_s), _p(anchors), _p(embed), _p(attrs),
+                                         _p(sets), _p(sims), _p(choice), B, T, F, E, int(k), A, _p(ws), ws.numel(),
+                                         _stream()), 'proj_anchor')
+    _count(2)
+    return (embed, attrs, sets, sims, choice) if return_all else (embed, attrs)
+
+
 def _embed_flat(embed):
     embed = _req(embed, 'embed')
     if embed.dim() == 4:

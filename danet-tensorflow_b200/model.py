@@ -41,6 +41,8 @@ class Model(object):
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
         self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
         self._ar_events = []
+        self._fuse_anchor = None          # inference: anchors handed to the encoder's projection (fused estimator sums)
+        self._fused_attrs = None          # (embedding, attractors) the fused projection produced
         self.step_count = 0
 
     # ---------------------------------------------------------------- variables
@@ -223,7 +225,27 @@ class Model(object):
             ent = self._packed[name] = (K.split_operand(W, True), K.colsum(W))
         w2, col_s = ent
         B, T, Kd = x.shape
+        if self._fuse_anchor is not None:
+            # the anchor estimator's sums are taken in this product's epilogue (danet_proj_anchor_fwd);
+            # AnchoredEstimator.__call__ picks the attractors up instead of launching its own pass over the embedding
+            E = hparams.EMBED_SIZE
+            embed, attrs = K.proj_anchor(prev[1], w2, B, T, W.shape[1] // E, E, Kd, self._fuse_anchor, row_mu=K.mean(x),
+                                         col_s=col_s)
+            self._fused_attrs = (embed, attrs)
+            return embed.view(B * T, W.shape[1])
         return K.gemm_split(prev[1], w2, B * T, W.shape[1], Kd, row_mu=K.mean(x), col_s=col_s, rows_per_mu=T)
+
+    USE_FUSED_PROJ_ANCHOR = True     # inference: projection + anchor-estimator sums in one kernel when the shapes allow
+
+    def _anchors_for_fusion(self):
+        """the infer estimator's anchors when the fused projection applies (exactly the `anchor` estimator, two sources,
+        E = 20, at most 6 anchors, tensor-core backend, variables already created), else None"""
+        est = self.infer_estimator
+        if (not self.USE_FUSED_PROJ_ANCHOR or self._tape is not None or K.DEFAULT_BACKEND != 1 or hparams.DEBUG
+                or type(est) is not _modules.AnchoredEstimator or hparams.MAX_N_SIGNAL != 2
+                or hparams.EMBED_SIZE != K.PROJ_ANCHOR_E or hparams.NUM_ANCHOR > 6 or not self.USE_CENTER_FOLD):
+            return None
+        return self.params.get('%s/anchors' % est.name)      # None on the very first call: creation order is the reference's
 
     def dense(self, name, x2, W, bias=None):
         """x2 [M,K] @ W (+ bias) with the weight operand split once and cached (inference)"""
@@ -455,7 +477,12 @@ class Model(object):
             logmag, mix_pwr = feats['logmag'], feats['mix_pwr']
         else:
             mix_pwr = None
-        embed = self.encoder(logmag)
+        self._fused_attrs = None
+        self._fuse_anchor = self._anchors_for_fusion()
+        try:
+            embed = self.encoder(logmag)
+        finally:
+            self._fuse_anchor = None
         K.stamp('proj')
         embed_flat = embed.view(B, T * F, -1)
         attrs = self.infer_estimator(embed, s_embed_flat=embed_flat)

@@ -332,6 +332,12 @@ class AnchoredEstimator(Estimator):
         return self.model.get_variable('%s/anchors' % self.name, [hparams.NUM_ANCHOR, hparams.EMBED_SIZE], _normal)
 
     def __call__(self, s_embed, s_src_pwr=None, s_mix_pwr=None, s_embed_flat=None):
+        fused = self.model._fused_attrs
+        if fused is not None:
+            # the encoder's output projection already took this estimator's sums in its epilogue (Model.centered_projection)
+            self.model._fused_attrs = None
+            if type(self) is AnchoredEstimator and fused[0].data_ptr() == s_embed.data_ptr():
+                return fused[1]
         if hparams.DEBUG:
             out, sets, sims, choice = K.attractor_anchor(s_embed, self.anchors(), hparams.MAX_N_SIGNAL, True)
             self.debug_fetches.update(asets=sets, anchors=self.anchors(), subset_choice=choice)

@@ -135,6 +135,25 @@ int danet_gemm_split(const void* A2, const void* B2, const float* bias, const fl
                      const float* col_s, int rows_per_mu, float* C, long long ldc,
                      int M, int N, int K, int out_perm_T, int accumulate, void* stream);
 
+/* ---- K2c + K3 fused: output projection with the anchor estimator's sums in its epilogue ----
+ * replaces, in ONE kernel + a per-utterance finalize, the mean-centred bias-free output layer of the encoder
+ * (app/modules.py:244-259: V = (x - mean_b(x)) W, reshaped [B,T,F,E]) AND AnchoredEstimator for two sources
+ * (app/modules.py:501-545 with C = 2: pair softmax eq.6, weighted means eq.7, similarity eq.8, argmin eq.9).
+ * The embedding is still written (the separator reads it), but the estimator never reads it back: each 128 x 160
+ * tcgen05 output tile (8 whole bins of E = 20) is turned into its contribution to sum S V / sum S while it sits in
+ * the epilogue warps' shared memory, on the tensor cores (mma.sync 3xTF32).
+ *   A2 [2*B*T, Kp], W2 [2*F*E, Kp]   split operands (danet_split_operand / danet_lstm_seq_fwd out_split)
+ *   row_mu [B] (nullable) + col_s [F*E]   the centring term, as danet_gemm_split
+ *   anchors [n_anchor, E]; embed [B, T*F, E] out; attractors [B,2,E] out; attractor_sets [B,P,2,E],
+ *   similarities [B,P], choice [B] (int32) nullable outputs, P = n_anchor (n_anchor - 1) / 2
+ * E must be 20 and n_anchor <= 6 (the configuration BASELINE.json benchmarks); anything else returns DANET_E_SHAPE
+ * and the caller uses danet_gemm_split + danet_attractor_anchor_fwd.  Deterministic (partials indexed by tile). */
+size_t danet_proj_anchor_workspace_bytes(int B, int T, int F, int E);
+int danet_proj_anchor_fwd(const void* A2, const void* W2, const float* row_mu, const float* col_s,
+                          const float* anchors, float* embed, float* attractors, float* attractor_sets,
+                          float* similarities, int* choice, int B, int T, int F, int E, int K, int n_anchor,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2b  (Bi)LSTM sequence kernel ----------------------------------------
  * replaces Model.lyr_lstm (main.py:76-132: tf.scan from zero state) over
  * ops.lyr_lstm_flat (app/ops.py:139-147: gates [cand|i|f|o], candidate WITHOUT tanh,

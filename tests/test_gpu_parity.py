@@ -735,3 +735,74 @@ def test_separate_host_pinned_io(D):
         model.separate_host(wav, out)
         torch.cuda.synchronize()
         assert float((out - ref).abs().max()) == 0.
+
+
+# ---------------------------------------------------------------- K2c + K3 fused
+@pytest.mark.parametrize('B,T,Kd,A', [(3, 140, 600, 6), (2, 5, 64, 6), (1, 501, 600, 6), (9, 129, 600, 4), (2, 128, 100, 3)])
+def test_proj_anchor_fused(K, B, T, Kd, A):
+    """danet_proj_anchor_fwd: V = (x - mean_b x) W with the anchor estimator's sums taken in the product's epilogue,
+    against float64 for the embedding and the oracle's estimator_anchor (app/modules.py:501-545) for sets / similarities /
+    choice / attractors; and against the unfused pair of kernels"""
+    F, E = 129, 20
+    rs = np.random.RandomState(B * 1000 + T)
+    x = (rs.standard_normal((B, T, Kd)) * .4 + .1).astype(np.float32)
+    W = rs.uniform(-1.85, 1.85, (Kd, F * E)).astype(np.float32) / np.sqrt(Kd / 8.)
+    anchors = rs.standard_normal((A, E)).astype(np.float32)
+    xg, Wg, ag = cuda(x), cuda(W), cuda(anchors)
+    a2 = K.split_operand(xg.view(B * T, Kd), False)
+    w2 = K.split_operand(Wg, True)
+    embed, attrs, sets, sims, choice = K.proj_anchor(a2, w2, B, T, F, E, Kd, ag, row_mu=K.mean(xg), col_s=K.colsum(Wg),
+                                                     return_all=True)
+    xc = x.astype(np.float64) - x.astype(np.float64).mean(axis=(1, 2), keepdims=True)
+    V = (xc.reshape(B * T, Kd) @ W.astype(np.float64)).reshape(B, T, F, E)
+    assert rel(embed, V) < 3e-5
+    ref, rsets, rsim, rchoice = O.estimator_anchor(torch.from_numpy(V), torch.from_numpy(anchors).double(), 2,
+                                                   return_all=True)
+    assert rel(sets, rsets) < 1e-4
+    assert rel(sims, rsim) < 1e-4
+    s = np.sort(rsim.numpy(), axis=1)
+    clear = (s[:, 1] - s[:, 0]) > 1e-3 * np.abs(s[:, 0])
+    assert np.array_equal(choice.cpu().numpy()[clear], rchoice.numpy()[clear])
+    if clear.all():
+        assert rel(attrs, ref) < 1e-4
+    # the unfused pair on the same operands: same embedding bit for bit is not required (different tile shape), 1e-6 is
+    v2 = K.gemm_split(a2, w2, B * T, F * E, Kd, row_mu=K.mean(xg), col_s=K.colsum(Wg), rows_per_mu=T)
+    assert rel(embed.view(B * T, F * E), v2) < 2e-6
+    assert rel(attrs, K.attractor_anchor(embed, ag, 2)) < 2e-5 or not clear.all()
+    # without the centring term
+    e0, a0 = K.proj_anchor(a2, w2, B, T, F, E, Kd, ag)
+    assert rel(e0, (x.astype(np.float64).reshape(B * T, Kd) @ W.astype(np.float64)).reshape(B, T, F, E)) < 3e-5
+    # deterministic: partials are indexed by tile, not by the CTA that happened to run the tile
+    e1, a1 = K.proj_anchor(a2, w2, B, T, F, E, Kd, ag, row_mu=K.mean(xg), col_s=K.colsum(Wg))
+    assert torch.equal(e1, embed) and torch.equal(a1, attrs)
+
+
+def test_proj_anchor_rejects_other_embedding_sizes(K):
+    a2 = torch.zeros(2 * 8, 64, dtype=torch.bfloat16, device='cuda')
+    w2 = torch.zeros(2 * 129 * 40, 64, dtype=torch.bfloat16, device='cuda')
+    with pytest.raises(ValueError):
+        K.proj_anchor(a2, w2, 2, 4, 129, 40, 64, torch.zeros(6, 40, device='cuda'))
+
+
+def test_fused_inference_path_equals_unfused(D):
+    """Model.infer with the fused projection (the default) against the same model with the fusion switched off: the
+    separate attractor launch is gone, the separated waveforms agree to fp32 rounding of the sums"""
+    _set_hparams(D, ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+                 SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=4)
+    K = D.kernels
+    model = D.Model('fuse').build()
+    wav = _shaped_noise(4, 8000, 21)
+    model.separate(wav)                                  # first call creates the variables (unfused by design)
+    calls = []
+    raw = K.attractor_anchor
+    K.attractor_anchor = lambda *a, **kw: (calls.append(1), raw(*a, **kw))[1]
+    try:
+        fused = model.separate(wav)
+        assert not calls                                 # no separate estimator pass
+        D.Model.USE_FUSED_PROJ_ANCHOR = False
+        plain = model.separate(wav)
+        assert calls
+    finally:
+        K.attractor_anchor = raw
+        D.Model.USE_FUSED_PROJ_ANCHOR = True
+    assert float((fused - plain).abs().max() / plain.abs().max()) < 1e-5

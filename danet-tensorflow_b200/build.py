@@ -15,13 +15,34 @@ def sources():
     return sorted(glob.glob(os.path.join(HERE, 'csrc', '*.cu')))
 
 
-def stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(HERE, 'csrc', '*.cuh')) + \
+INFO = os.path.join(HERE, 'lib', 'build_info.json')
+
+
+def source_hash():
+    """sha256 over every source the library is built from (+ the compiler flags): what `build()` records next to the
+    .so, so a shipped binary can be told apart from one that no longer matches the tree"""
+    import hashlib
+    h = hashlib.sha256(' '.join(FLAGS).encode())
+    deps = sources() + sorted(glob.glob(os.path.join(HERE, 'csrc', '*.cuh'))) + \
         [os.path.join(os.path.dirname(HERE), 'include', 'danet.h')]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, 'rb').read())
+    return h.hexdigest()
+
+
+def built_hash():
+    import json
+    try:
+        return json.load(open(INFO)).get('source_sha256')
+    except Exception:
+        return None
+
+
+def stale():
+    """True when there is no library or it was built from other sources than the tree holds now (content hash, not
+    modification times: a snapshot copied to the GPU box has fresh mtimes on every file)"""
+    return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -48,6 +69,11 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s' % r.stdout.decode())
+    import json
+    import time
+    with open(INFO, 'w') as f:
+        json.dump({'source_sha256': source_hash(), 'flags': FLAGS, 'nvcc': NVCC, 'built_at': time.strftime('%Y-%m-%dT%H:%M:%SZ', time.gmtime()),
+                   'sources': [os.path.basename(x) for x in sources()]}, f, indent=1)
     return LIB
 
 

@@ -408,7 +408,11 @@ attractor_anchor2_mma_kernel(const float* __restrict__ embed, const float* __res
     mbar_wait_parity(&bars[warp][buf], (uint32_t)(it >> 1) & 1);
     const long long bin0 = c * kMmaChunk;
     const int n_here = (int)(TF - bin0 < kMmaChunk ? TF - bin0 : kMmaChunk);
-    const float* tile = &sV[warp][buf][0];
+    float* tile = &sV[warp][buf][0];
+    if (n_here < kMmaChunk) {                              // last chunk of the utterance: clear the rows that were not copied
+      for (int i = n_here * kMmaE + lane; i < kMmaChunk * kMmaE; i += 32) tile[i] = 0.f;
+      __syncwarp();
+    }
 
     // ---- the six anchor logits of bin (bin0 + lane): 5 x LDS.128 of the bin's row (row stride 20 floats: conflict-free)
     {
@@ -435,39 +439,40 @@ attractor_anchor2_mma_kernel(const float* __restrict__ embed, const float* __res
     }
     __syncwarp();
 
-    // ---- acc[16 x 24] += S^T[16 x 32] * [V | 1 | 0][32 x 24], four k8 steps
+    // ---- acc[16 x 24] += S^T[16 x 32] * [V | 1 | 0][32 x 24], four k8 steps.  The 16 sigmoids of this lane's A fragments
+    // (a0 (row gid, bin tig), a1 (row gid+8, bin tig), a2 (row gid, bin tig+4), a3 (row gid+8, bin tig+4) per step) are
+    // evaluated first as independent chains, then the 36 MMAs follow.
+    float sv[4][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      // A fragment: a0 (row gid, bin tig), a1 (row gid+8, bin tig), a2 (row gid, bin tig+4), a3 (row gid+8, bin tig+4)
-      uint32_t ahi[4], alo[4];
+    for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int k = 8 * ks + tig + 4 * j;
-        const bool ok = k < n_here;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float sv;
-          if (kind[h] == 0) {
-            // softmax over the pair (a, b): S_a = 1 / (1 + exp(l_b - l_a))   (eq.6 with C = 2)
-            const float d = sL[warp][k][pb[h]] - sL[warp][k][pa[h]];
-            sv = __fdividef(1.f, 1.f + __expf(d));
-          } else {
-            sv = kind[h] == 1 ? 1.f : 0.f;
-          }
-          if (!ok) sv = 0.f;
-          split_tf32(sv, ahi[2 * j + h], alo[2 * j + h]);
+          // softmax over the pair (a, b): S_a = 1 / (1 + exp(l_b - l_a))   (eq.6 with C = 2)
+          const float d = sL[warp][k][pb[h]] - sL[warp][k][pa[h]];
+          float x = __fdividef(1.f, 1.f + __expf(d));
+          x = kind[h] == 0 ? x : (kind[h] == 1 ? 1.f : 0.f);
+          sv[ks][2 * j + h] = k < n_here ? x : 0.f;
         }
       }
 #pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_tf32(sv[ks][i], ahi[i], alo[i]);
+#pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
-        // B fragment: b0 (bin tig, column 8 nt + gid), b1 (bin tig + 4, same column); column 20 is the constant 1
-        const int n = 8 * nt + gid;
+        // B fragment: b0 (bin tig, column 8 nt + gid), b1 (bin tig + 4, same column); column 20 is the constant 1.
+        // Bins beyond the end carry a zero weight in A and zeros here (the tail chunk's buffer was cleared above).
         uint32_t bhi[2], blo[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int k = 8 * ks + tig + 4 * j;
-          float x = 0.f;
-          if (k < n_here) x = n < kMmaE ? tile[k * kMmaE + n] : (n == kMmaE ? 1.f : 0.f);
+          float x;
+          if (nt < 2) x = tile[k * kMmaE + 8 * nt + gid];
+          else x = gid < 4 ? tile[k * kMmaE + 16 + gid] : (gid == 4 ? 1.f : 0.f);
           split_tf32(x, bhi[j], blo[j]);
         }
         mma_tf32(acc[nt], alo, bhi[0], bhi[1]);        // small terms first
@@ -528,10 +533,11 @@ attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, i
     for (int i = tid; i < n_sub * ld; i += 256) {
       const int s = i / ld, e = i % ld;
       float first = 0.f, total = 0.f;
-      for (int pt = 0; pt < n_parts; ++pt) {
-        const float* pp = part + ((size_t)b * n_parts + pt) * np;
-        first += pp[s * ld + e];
-        total += pp[n_sub * ld + e];
+      const float* pp = part + (size_t)b * n_parts * np;
+#pragma unroll 8
+      for (int pt = 0; pt < n_parts; ++pt) {               // independent loads: unrolled so they are all in flight
+        first += __ldg(pp + (size_t)pt * np + s * ld + e);
+        total += __ldg(pp + (size_t)pt * np + n_sub * ld + e);
       }
       s_sum[(2 * s) * ld + e] = first;
       s_sum[(2 * s + 1) * ld + e] = total - first;
@@ -539,7 +545,9 @@ attractor_finalize_kernel(const float* __restrict__ part, int C, int E, int R, i
   } else {
     for (int i = tid; i < n; i += 256) {
       float s = 0.f;
-      for (int pt = 0; pt < n_parts; ++pt) s += part[((size_t)b * n_parts + pt) * n + i];
+      const float* pp = part + (size_t)b * n_parts * n + i;
+#pragma unroll 8
+      for (int pt = 0; pt < n_parts; ++pt) s += __ldg(pp + (size_t)pt * n);
       s_sum[i] = s;
     }
   }

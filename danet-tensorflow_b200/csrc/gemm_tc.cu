@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by an offset into the __shared__ array: derived pointers keep the shared address space (LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;        // [2]
@@ -373,7 +374,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
 proj_anchor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const ProjAnchorParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by an OFFSET into the __shared__ array (not by integer arithmetic on the pointer value), so every pointer
+  // derived below keeps its shared address space and compiles to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes);
   uint64_t* empty_bar = full_bar + kPStages;
   uint64_t* tmem_full_bar = empty_bar + kPStages;       // [2]
@@ -574,37 +577,41 @@ proj_anchor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             *reinterpret_cast<float4*>(p.V + (g0 + r) * (size_t)p.N + n0 + c0 + 4 * part4) =
                 *reinterpret_cast<const float4*>(tile + r * kPPair + 4 * part4);
         }
-        // (b) acc[16 x 24] += S^T[16 x 32 rows] * [V_bin | 1 | 0][32 rows x 24] for each bin of the pair
+        // (b) acc[16 x 24] += S^T[16 x 32 rows] * [V_bin | 1 | 0][32 rows x 24] for each bin of the pair.
+        // The 16 pair sigmoids this lane's A fragments hold (4 k8 steps x 4) are evaluated first, as 16 independent
+        // chains (the epilogue has two warps per scheduler: instruction-level parallelism is what hides the MUFU and
+        // shared-memory latencies), then the 36 MMAs follow with their B fragments.
         for (int bs = 0; bs < nbin; ++bs) {
+          float sv[4][4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = 8 * ks + tig + 4 * j;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                // softmax over the pair (a, b): S_a = 1 / (1 + exp(l_b - l_a))   (eq.6 with C = 2)
+                const float d = sL[k * kPLdL + 8 * bs + pb[h]] - sL[k * kPLdL + 8 * bs + pa[h]];
+                float x = __fdividef(1.f, 1.f + __expf(d));
+                x = kind[h] == 0 ? x : (kind[h] == 1 ? 1.f : 0.f);
+                sv[ks][2 * j + h] = k < n_here ? x : 0.f;
+              }
+            }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             uint32_t ahi[4], alo[4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int k = 8 * ks + tig + 4 * j;
-              const bool ok = k < n_here;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                float sv;
-                if (kind[h] == 0) {
-                  const float d = sL[k * kPLdL + 8 * bs + pb[h]] - sL[k * kPLdL + 8 * bs + pa[h]];
-                  sv = __fdividef(1.f, 1.f + __expf(d));
-                } else {
-                  sv = kind[h] == 1 ? 1.f : 0.f;
-                }
-                if (!ok) sv = 0.f;
-                split_tf32(sv, ahi[2 * j + h], alo[2 * j + h]);
-              }
-            }
+            for (int i = 0; i < 4; ++i) split_tf32(sv[ks][i], ahi[i], alo[i]);
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-              const int n = 8 * nt + gid;
+              // rows beyond the utterance carry a zero weight in A and finite values here: no mask needed
               uint32_t bhi[2], blo[2];
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 const int k = 8 * ks + tig + 4 * j;
-                float x = 0.f;
-                if (k < n_here) x = n < kPE ? tile[k * kPPair + kPE * bs + n] : (n == kPE ? 1.f : 0.f);
+                float x;
+                if (nt < 2) x = tile[k * kPPair + kPE * bs + 8 * nt + gid];
+                else x = gid < 4 ? tile[k * kPPair + kPE * bs + 16 + gid] : (gid == 4 ? 1.f : 0.f);
                 split_tf32(x, bhi[j], blo[j]);
               }
               mma_tf32(acc[nt], alo, bhi[0], bhi[1]);

@@ -535,6 +535,7 @@ lstm_tc2_kernel(const LstmTcParams p) {
     // ================= MMA issuer =================
     if (elect_one_sync()) {
       constexpr uint32_t idesc = HF ? umma_idesc_f16(kRows, kUmmaN) : umma_idesc_bf16(kRows, kUmmaN);
+      const int j_full = (H - (ncta - 1) * kUnits > 16) ? ncta : ncta - 1;      // K blocks with both K16 slices in use
       for (int s = 1; s < T; ++s) {
         const int buf = (s - 1) & 1;
         const uint64_t b0d = umma_desc_k_sw64_sbo512(smem_u32(sH + (size_t)buf * ncta * kBlk));
@@ -543,7 +544,7 @@ lstm_tc2_kernel(const LstmTcParams p) {
         DANET_PROF(1);
         tc_fence_after();
 #pragma unroll 2
-        for (int j = 0; j < ncta; ++j) {
+        for (int j = 0; j < j_full; ++j) {
           // HF 0: rows 0-7 lo, rows 8-15 hi for A_hi; rows 0-7 hi, rows 8-15 zero for A_lo.  HF 1: [h | zero] for both.
           const uint64_t b_first = b0d + (uint64_t)((j * kBlk) >> 4);
           const uint64_t b_second = HF ? b_first : b_first + (uint64_t)(512 >> 4);
@@ -554,6 +555,16 @@ lstm_tc2_kernel(const LstmTcParams p) {
             umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_first + adv, idesc, (j | k) != 0);
             umma_bf16_ts(tmem_acc, tmem_a_lo + ac, b_second + adv, idesc, 1);
           }
+        }
+        if (j_full < ncta) {
+          // the last CTA's block holds fewer than 17 real units (H = 300: units 288..299): its second K16 slice multiplies
+          // zero weights by zero state and is not issued -- 38 MMAs per step instead of 40.  (Peeled out of the loop above:
+          // a conditional inside it cost 220 cycles per step by breaking the unrolled issue sequence.)
+          const int j = ncta - 1;
+          const uint64_t b_first = b0d + (uint64_t)((j * kBlk) >> 4);
+          const uint64_t b_second = HF ? b_first : b_first + (uint64_t)(512 >> 4);
+          umma_bf16_ts(tmem_acc, tmem_a_hi + (uint32_t)(j * 16), b_first, idesc, j != 0);
+          umma_bf16_ts(tmem_acc, tmem_a_lo + (uint32_t)(j * 16), b_second, idesc, 1);
         }
         umma_commit(acc_full);
         DANET_PROF(2);

@@ -6,14 +6,14 @@
 
 namespace danet {
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round to the 10-bit TF32 mantissa: add half an ulp of the kept part, clear the dropped 13 bits (round half away from
+// zero in magnitude, as cvt.rna.tf32; two integer instructions where the cvt expands to a NaN-safe sequence of eight --
+// the operands here are finite by construction)
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// x = hi + lo with hi exactly representable in TF32; the tensor core ignores the low 13 bits of lo (a 2^-21 effect)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // D[16x8] += A[16x8] * B[8x8]; fragments as in the PTX ISA (gid = lane / 4, tig = lane % 4):
 //   a0 (row gid, k tig), a1 (row gid + 8, k tig), a2 (row gid, k tig + 4), a3 (row gid + 8, k tig + 4)

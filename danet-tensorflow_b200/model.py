@@ -41,6 +41,7 @@ class Model(object):
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
         self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
         self._ar_events = []
+        self._vars_ready = False          # every variable exists (created in the reference's order)
         self._fuse_anchor = None          # inference: anchors handed to the encoder's projection (fused estimator sums)
         self._fused_attrs = None          # (embedding, attractors) the fused projection produced
         self.step_count = 0
@@ -245,7 +246,20 @@ class Model(object):
                 or type(est) is not _modules.AnchoredEstimator or hparams.MAX_N_SIGNAL != 2
                 or hparams.EMBED_SIZE != K.PROJ_ANCHOR_E or hparams.NUM_ANCHOR > 6 or not self.USE_CENTER_FOLD):
             return None
-        return self.params.get('%s/anchors' % est.name)      # None on the very first call: creation order is the reference's
+        self._ensure_variables()
+        return self.params.get('%s/anchors' % est.name)
+
+    def _ensure_variables(self):
+        """very first inference call: create every variable in the reference's order (encoder, train estimator, infer
+        estimator: main.py:210-270) with the 4-frame dry run of reset(), so that the first call already takes the same
+        (fused) path as every later one"""
+        if self._vars_ready:
+            return
+        pending, self._stagger_pending = self._stagger_pending, False
+        fuse, self._fuse_anchor = self._fuse_anchor, None
+        self._vars_ready = True
+        self.reset()
+        self._stagger_pending, self._fuse_anchor = pending, fuse
 
     def dense(self, name, x2, W, bias=None):
         """x2 [M,K] @ W (+ bias) with the weight operand split once and cached (inference)"""
@@ -499,6 +513,7 @@ class Model(object):
         ordering between the streams."""
         if self._packed_ready or self._tape is not None:
             return
+        self._ensure_variables()
         T0 = max(4, int(getattr(self.encoder, 'TIME_ALIGN', 1) or 1))
         pending, self._stagger_pending = self._stagger_pending, False
         self._last_split = None
@@ -644,16 +659,27 @@ class Model(object):
 
     LSTM_PRIORITY_STREAM = True        # measured: 2.862 -> 2.838 ms per step (tools/ab_groups.py)
 
+    # Stream priorities of the grouped inference step: every recurrence launches from the highest level (its clusters
+    # need whole SMs and carry the critical path); among the groups' own streams the EARLIER group outranks the later
+    # one, so that at the end of the step -- four projections / mask kernels contending for the SMs the last
+    # recurrences have not freed yet -- the groups finish in start order, a copy time apart, instead of in a convoy whose
+    # device-to-host copies then queue on the link.
+    GROUP_PRIORITIES = True
+
     def _priority_twin(self, stream):
         tw = self._twins.get(stream.cuda_stream)
         if tw is None:
-            tw = self._twins[stream.cuda_stream] = torch.cuda.Stream(device=self.device, priority=-1)
+            tw = self._twins[stream.cuda_stream] = torch.cuda.Stream(device=self.device,
+                                                                     priority=-3 if self.GROUP_PRIORITIES else -1)
         return tw
 
     def _side_streams(self, n):
         pool = self._streams
         while len(pool) < n:
-            pool.append(torch.cuda.Stream(device=self.device))
+            g = len(pool)
+            # torch's stream pools expose four levels (0 .. -3): the recurrences take -3, the groups -2, -1, 0, 0
+            prio = min(0, -2 + g) if self.GROUP_PRIORITIES else 0
+            pool.append(torch.cuda.Stream(device=self.device, priority=prio))
         return pool[:n]
 
     def separate_host(self, wav_host, out_host=None, graphed=True):

@@ -79,19 +79,18 @@ class StreamingSeparator(object):
             raise ValueError('window is longer than input signal (%d < %d)' % (self.n, K.FFT_SIZE))
         model = self.model
         T = K.num_frames(self.n)
-        Cn, E = hparams.MAX_N_SIGNAL, hparams.EMBED_SIZE
+        Cn = hparams.MAX_N_SIGNAL
         self._transform(self.t_done, T, self.n)        # the tail sees the true right padding: same call as the batch path
-        mix, logmag = self.mix[:, :T], self.logmag[:, :T]
-        embed = model.encoder(logmag.contiguous())
-        flat = embed.view(1, T * K.FEATURE, E)
-        attrs = model.infer_estimator(embed, s_embed_flat=flat)
+        mix, logmag = self.mix[:, :T].contiguous(), self.logmag[:, :T].contiguous()
         if out_host is None:
             out_host = torch.empty((Cn, HOP * T), dtype=torch.float32).pin_memory()
         events = []
         cur = torch.cuda.current_stream()
-        # utils.istft semantics (last 4 frames unused, division by the window power) depend on the absolute frame index:
-        # K4 runs once over the utterance (tens of microseconds) and the blocks are cut from its output
-        wav_dev = model.separator(None, attrs, flat, s_mixed_signals=mix.contiguous(), want=('wav',))['wav'][0]
+        # the same call Model.separate makes per stream group: encoder (with the estimator's sums fused into its output
+        # projection when the shapes allow) -> attractors -> K4.  utils.istft semantics (last 4 frames unused, division by
+        # the window power) depend on the absolute frame index, so K4 runs once over the utterance (tens of microseconds)
+        # and the blocks are cut from its output
+        wav_dev = model.infer(mix, logmag=logmag, want='wav')[0]
         step = HOP * self.out_block
         self.copy_stream.wait_event(cur.record_event())
         with torch.cuda.stream(self.copy_stream):

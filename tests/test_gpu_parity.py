@@ -746,7 +746,7 @@ def test_proj_anchor_fused(K, B, T, Kd, A):
     F, E = 129, 20
     rs = np.random.RandomState(B * 1000 + T)
     x = (rs.standard_normal((B, T, Kd)) * .4 + .1).astype(np.float32)
-    W = rs.uniform(-1.85, 1.85, (Kd, F * E)).astype(np.float32) / np.sqrt(Kd / 8.)
+    W = (rs.uniform(-1.85, 1.85, (Kd, F * E)) / np.sqrt(Kd / 8.)).astype(np.float32)
     anchors = rs.standard_normal((A, E)).astype(np.float32)
     xg, Wg, ag = cuda(x), cuda(W), cuda(anchors)
     a2 = K.split_operand(xg.view(B * T, Kd), False)
@@ -792,7 +792,7 @@ def test_fused_inference_path_equals_unfused(D):
     K = D.kernels
     model = D.Model('fuse').build()
     wav = _shaped_noise(4, 8000, 21)
-    model.separate(wav)                                  # first call creates the variables (unfused by design)
+    model.separate(wav)
     calls = []
     raw = K.attractor_anchor
     K.attractor_anchor = lambda *a, **kw: (calls.append(1), raw(*a, **kw))[1]

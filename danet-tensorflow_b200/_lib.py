@@ -69,6 +69,9 @@ PROTOTYPES = {
     'danet_istft_fwd': (c_i, [c_f, c_i, c_i, c_f, c_v]),
     'danet_conv2d_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, C.c_float, c_v]),
     'danet_maxpool2x2_fwd': (c_i, [c_f, c_f, c_ll, c_i, c_i, c_v]),
+    'danet_conv2d_bwd_data': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_v]),
+    'danet_conv2d_bwd_weights': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_v]),
+    'danet_maxpool2x2_bwd': (c_i, [c_f, c_f, c_f, c_ll, c_i, c_i, c_v]),
     'danet_add_fwd': (c_i, [c_f, c_f, c_f, c_ll, c_v]),
     'danet_mask_cmul_istft_fwd': (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_v]),
     'danet_pit_workspace_bytes': (c_sz, [c_i, c_i]),

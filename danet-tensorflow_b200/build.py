@@ -9,6 +9,8 @@ LIB = os.path.join(HERE, 'lib', 'libdanet_sm100.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+# experiment builds (e.g. DANET_NVCC_EXTRA=-DDANET_LSTM_PRE_DEPTH=3): part of the recorded hash, so a change rebuilds
+FLAGS += [f for f in os.environ.get('DANET_NVCC_EXTRA', '').split() if f]
 
 
 def sources():

@@ -15,7 +15,12 @@ constexpr int kCvCo = 16;                  // output channels per block
 constexpr int kCvCi = 8;                   // input channels per staged chunk
 constexpr int kCvMaxK = 5;
 
-template <int KS>
+// WT = true: the DATA GRADIENT of the same layer.  dX[ci][u][v] = sum_{co,kh,kw} dY[co][u-kh+R][v-kw+R] W[kh][kw][ci][co]
+// is again a 'same' convolution -- of dY (Cout channels in) to Cin channels out, with the kernel flipped in both spatial
+// axes and its two channel axes swapped -- so the kernel is shared and only the weight staging differs: it reads the
+// forward layer's [kh][kw][Cin][Cout] array in place (here `Cin` / `Cout` are this launch's in / out channel counts, i.e.
+// the forward layer's Cout / Cin).
+template <int KS, bool WT = false>
 __global__ void __launch_bounds__(kCvTW * kCvTH)
 conv2d_same_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ y, int Cin, int Cout, int H, int W, float leak) {
@@ -42,7 +47,10 @@ conv2d_same_kernel(const float* __restrict__ x, const float* __restrict__ w, con
     }
     for (int i = threadIdx.x; i < KS * KS * nci * kCvCo; i += kCvTW * kCvTH) {
       const int co = i % kCvCo, c = (i / kCvCo) % nci, kk = i / (kCvCo * nci);
-      s_w[kk * kCvCi + c][co] = co0 + co < Cout ? __ldg(w + ((size_t)kk * Cin + ci0 + c) * Cout + co0 + co) : 0.f;
+      if (WT)
+        s_w[kk * kCvCi + c][co] = co0 + co < Cout ? __ldg(w + ((size_t)(KS * KS - 1 - kk) * Cout + co0 + co) * Cin + ci0 + c) : 0.f;
+      else
+        s_w[kk * kCvCi + c][co] = co0 + co < Cout ? __ldg(w + ((size_t)kk * Cin + ci0 + c) * Cout + co0 + co) : 0.f;
     }
     __syncthreads();
     for (int c = 0; c < nci; ++c)
@@ -83,6 +91,83 @@ maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, long long 
     const long long img = i / ((long long)Wo * Ho);
     const float* p = x + (img * H + 2 * yo) * W + 2 * xo;
     y[i] = fmaxf(fmaxf(__ldg(p), __ldg(p + 1)), fmaxf(__ldg(p + W), __ldg(p + W + 1)));
+  }
+}
+
+
+// Weight and bias gradients of the same layer (TF autodiff of tf.layers.conv2d, main.py:357-358):
+//   dW[kh][kw][ci][co] = sum_{b,y,x} X[b][ci][y+kh-R][x+kw-R] dY[b][co][y][x],   db[co] = sum_{b,y,x} dY[b][co][y][x]
+// One block per (ci, co): every thread walks the output pixels with a fixed stride and keeps the KS x KS taps in
+// registers; fixed-order block reduction (deterministic).  This encoder's training step is not a benchmarked path.
+template <int KS>
+__global__ void __launch_bounds__(256)
+conv2d_bwd_weights_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                          float* __restrict__ db, int B, int Cin, int Cout, int H, int W) {
+  constexpr int R = KS / 2;
+  const int ci = blockIdx.x, co = blockIdx.y;
+  float acc[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  const long long HW = (long long)H * W, total = (long long)B * HW;
+  for (long long i = threadIdx.x; i < total; i += 256) {
+    const int b = (int)(i / HW), yy = (int)((i % HW) / W), xx = (int)(i % W);
+    const float g = __ldg(dy + ((size_t)b * Cout + co) * HW + (size_t)yy * W + xx);
+    bsum += g;
+    const float* xp = x + ((size_t)b * Cin + ci) * HW;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const int sy = yy + kh - R;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const int sx = xx + kw - R;
+        if (sx >= 0 && sx < W) acc[kh * KS + kw] = fmaf(__ldg(xp + (size_t)sy * W + sx), g, acc[kh * KS + kw]);
+      }
+    }
+  }
+  __shared__ float red[8][KS * KS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  {
+    const float v = warp_sum(bsum);
+    if (lane == 0) red[warp][KS * KS] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= KS * KS) {
+    float v = 0.f;
+    for (int wq = 0; wq < 8; ++wq) v += red[wq][threadIdx.x];
+    if (threadIdx.x < KS * KS) dw[((size_t)threadIdx.x * Cin + ci) * Cout + co] = v;
+    else if (ci == 0 && db) db[co] = v;
+  }
+}
+
+// gradient of the 2 x 2 / stride 2 max pooling: the whole window gradient goes to the window's FIRST maximum (row-major),
+// as the argmax-based MaxPoolGrad does; a trailing odd row / column belongs to no window and gets zero
+__global__ void __launch_bounds__(256)
+maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n_img,
+                      int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = n_img * H * W;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xx = (int)(i % W), yy = (int)((i / W) % H);
+    const long long img = i / ((long long)W * H);
+    const int yo = yy >> 1, xo = xx >> 1;
+    float g = 0.f;
+    if (yo < Ho && xo < Wo) {
+      const float* p = x + (img * H + 2 * yo) * W + 2 * xo;
+      const float v[4] = {__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1)};
+      int best = 0;
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q] > v[best]) best = q;
+      if (best == ((yy & 1) << 1 | (xx & 1))) g = __ldg(dy + (img * Ho + yo) * Wo + xo);
+    }
+    dx[i] = g;
   }
 }
 
@@ -136,6 +221,54 @@ extern "C" int danet_add_fwd(const float* a, const float* b, float* out, long lo
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   add_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a, b, out, n);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_conv2d_bwd_data(const float* dy, const float* w_hwio, float* dx, int B, int Cin, int Cout, int H, int W,
+                                     int ksize, void* stream) {
+  DANET_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, DANET_E_SHAPE, "conv2d_bwd_data: B %d Cin %d Cout %d H %d W %d",
+                B, Cin, Cout, H, W);
+  DANET_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, DANET_E_SHAPE, "conv2d_bwd_data: kernel size %d (1, 3 or 5)", ksize);
+  if (B == 0) return DANET_OK;
+  DANET_REQUIRE(dy && w_hwio && dx, DANET_E_ARG, "conv2d_bwd_data: null pointer");
+  const int co_blocks = (Cin + kCvCo - 1) / kCvCo;                 // this launch's output channels = the layer's Cin
+  DANET_REQUIRE((long long)B * co_blocks <= 65535, DANET_E_SHAPE, "conv2d_bwd_data: B x ceil(Cin/16) = %lld > 65535",
+                (long long)B * co_blocks);
+  dim3 grid((W + kCvTW - 1) / kCvTW, (H + kCvTH - 1) / kCvTH, B * co_blocks);
+  DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "conv2d_bwd_data: H %d too large", H);
+  cudaStream_t st = as_stream(stream);
+  if (ksize == 5) conv2d_same_kernel<5, true><<<grid, kCvTW * kCvTH, 0, st>>>(dy, w_hwio, nullptr, dx, Cout, Cin, H, W, -1.f);
+  else if (ksize == 3) conv2d_same_kernel<3, true><<<grid, kCvTW * kCvTH, 0, st>>>(dy, w_hwio, nullptr, dx, Cout, Cin, H, W, -1.f);
+  else conv2d_same_kernel<1, true><<<grid, kCvTW * kCvTH, 0, st>>>(dy, w_hwio, nullptr, dx, Cout, Cin, H, W, -1.f);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_conv2d_bwd_weights(const float* x, const float* dy, float* dw_hwio, float* dbias, int B, int Cin, int Cout,
+                                        int H, int W, int ksize, void* stream) {
+  DANET_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1 && Cout <= 65535, DANET_E_SHAPE,
+                "conv2d_bwd_weights: B %d Cin %d Cout %d H %d W %d", B, Cin, Cout, H, W);
+  DANET_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, DANET_E_SHAPE, "conv2d_bwd_weights: kernel size %d (1, 3 or 5)", ksize);
+  DANET_REQUIRE(x && dy && dw_hwio, DANET_E_ARG, "conv2d_bwd_weights: null pointer");
+  dim3 grid(Cin, Cout);
+  cudaStream_t st = as_stream(stream);
+  if (ksize == 5) conv2d_bwd_weights_kernel<5><<<grid, 256, 0, st>>>(x, dy, dw_hwio, dbias, B, Cin, Cout, H, W);
+  else if (ksize == 3) conv2d_bwd_weights_kernel<3><<<grid, 256, 0, st>>>(x, dy, dw_hwio, dbias, B, Cin, Cout, H, W);
+  else conv2d_bwd_weights_kernel<1><<<grid, 256, 0, st>>>(x, dy, dw_hwio, dbias, B, Cin, Cout, H, W);
+  DANET_LAUNCH_CHECK();
+  return DANET_OK;
+}
+
+extern "C" int danet_maxpool2x2_bwd(const float* x, const float* dy, float* dx, long long n_img, int H, int W, void* stream) {
+  DANET_REQUIRE(n_img >= 0 && H >= 2 && W >= 2, DANET_E_SHAPE, "maxpool2x2_bwd: n_img %lld H %d W %d", n_img, H, W);
+  if (n_img == 0) return DANET_OK;
+  DANET_REQUIRE(x && dy && dx, DANET_E_ARG, "maxpool2x2_bwd: null pointer");
+  const long long total = n_img * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  maxpool2x2_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, dy, dx, n_img, H, W);
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }

@@ -363,6 +363,10 @@ lstm_tc_kernel(const LstmTcParams p) {
 //     instead of 8;
 //   * Wh arrives pre-split (danet_lstm_pack_wh) through one bulk copy per CTA: prologue 45k -> 6k cycles.
 constexpr int kEpi2Warps = 8;
+#ifndef DANET_LSTM_PRE_DEPTH
+#define DANET_LSTM_PRE_DEPTH 2      // measured 2 / 3 / 4: profiles/r02_lstm_experiment_skip_zero_slice.txt
+#endif
+constexpr int kPreDepth = DANET_LSTM_PRE_DEPTH;
 constexpr int kEpi2Threads = 32 * kEpi2Warps;
 constexpr int kThreads2 = kEpi2Threads + 32 + 32 * kMaxCta;
 
@@ -535,7 +539,6 @@ lstm_tc2_kernel(const LstmTcParams p) {
     // ================= MMA issuer =================
     if (elect_one_sync()) {
       constexpr uint32_t idesc = HF ? umma_idesc_f16(kRows, kUmmaN) : umma_idesc_bf16(kRows, kUmmaN);
-      const int j_full = (H - (ncta - 1) * kUnits > 16) ? ncta : ncta - 1;      // K blocks with both K16 slices in use
       for (int s = 1; s < T; ++s) {
         const int buf = (s - 1) & 1;
         const uint64_t b0d = umma_desc_k_sw64_sbo512(smem_u32(sH + (size_t)buf * ncta * kBlk));
@@ -544,8 +547,11 @@ lstm_tc2_kernel(const LstmTcParams p) {
         DANET_PROF(1);
         tc_fence_after();
 #pragma unroll 2
-        for (int j = 0; j < j_full; ++j) {
+        for (int j = 0; j < ncta; ++j) {
           // HF 0: rows 0-7 lo, rows 8-15 hi for A_hi; rows 0-7 hi, rows 8-15 zero for A_lo.  HF 1: [h | zero] for both.
+          // (The last block's second K16 slice is all zeros at H = 300; NOT issuing it was measured: a conditional in this
+          // loop costs 220 cycles per step, peeling the last block 60 -- the unrolled issue sequence is worth more than
+          // two MMAs.  profiles/r02_lstm_experiment_skip_zero_slice.txt)
           const uint64_t b_first = b0d + (uint64_t)((j * kBlk) >> 4);
           const uint64_t b_second = HF ? b_first : b_first + (uint64_t)(512 >> 4);
 #pragma unroll
@@ -555,16 +561,6 @@ lstm_tc2_kernel(const LstmTcParams p) {
             umma_bf16_ts(tmem_acc, tmem_a_hi + ac, b_first + adv, idesc, (j | k) != 0);
             umma_bf16_ts(tmem_acc, tmem_a_lo + ac, b_second + adv, idesc, 1);
           }
-        }
-        if (j_full < ncta) {
-          // the last CTA's block holds fewer than 17 real units (H = 300: units 288..299): its second K16 slice multiplies
-          // zero weights by zero state and is not issued -- 38 MMAs per step instead of 40.  (Peeled out of the loop above:
-          // a conditional inside it cost 220 cycles per step by breaking the unrolled issue sequence.)
-          const int j = ncta - 1;
-          const uint64_t b_first = b0d + (uint64_t)((j * kBlk) >> 4);
-          const uint64_t b_second = HF ? b_first : b_first + (uint64_t)(512 >> 4);
-          umma_bf16_ts(tmem_acc, tmem_a_hi + (uint32_t)(j * 16), b_first, idesc, j != 0);
-          umma_bf16_ts(tmem_acc, tmem_a_lo + (uint32_t)(j * 16), b_second, idesc, 1);
         }
         umma_commit(acc_full);
         DANET_PROF(2);
@@ -579,7 +575,9 @@ lstm_tc2_kernel(const LstmTcParams p) {
     const int b = b0 + bl, unit = unit0 + ul;
     const bool valid = b < B && unit < H;
     float c = 0.f;
-    float pre_q[2][4];
+    // input projections are fetched kPreDepth steps ahead (they do not depend on the recurrence): under the stream-group
+    // schedule the other groups' dense products load L2, and a fetch that is late stalls all ten CTAs of the cluster
+    float pre_q[kPreDepth][4];
     auto load_pre = [&](int s, float (&dst)[4]) {
 #pragma unroll
       for (int gg = 0; gg < 4; ++gg) dst[gg] = 0.f;
@@ -590,8 +588,8 @@ lstm_tc2_kernel(const LstmTcParams p) {
         for (int gg = 0; gg < 4; ++gg) dst[gg] = __ldcg(qp + gg * H);
       }
     };
-    load_pre(0, pre_q[0]);
-    load_pre(1, pre_q[1]);
+#pragma unroll
+    for (int d = 0; d < kPreDepth; ++d) load_pre(d, pre_q[d]);
     const int outw = p.n_dir * H;
     const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
     const uint32_t stage_off = sw64_offset(bl, ul & ~1);      // the (even, odd) unit pair of utterance bl: 4 bytes
@@ -605,8 +603,12 @@ lstm_tc2_kernel(const LstmTcParams p) {
       const int to = dir ? T - 1 - s : s;
       float a[4];
 #pragma unroll
-      for (int gg = 0; gg < 4; ++gg) { a[gg] = pre_q[0][gg]; pre_q[0][gg] = pre_q[1][gg]; }
-      load_pre(s + 2, pre_q[1]);
+      for (int gg = 0; gg < 4; ++gg) {
+        a[gg] = pre_q[0][gg];
+#pragma unroll
+        for (int d = 0; d + 1 < kPreDepth; ++d) pre_q[d][gg] = pre_q[d + 1][gg];
+      }
+      load_pre(s + kPreDepth, pre_q[kPreDepth - 1]);
       DANET_PROF(3);
       if (s > 0) {
         mbar_wait(acc_full, (s - 1) & 1);

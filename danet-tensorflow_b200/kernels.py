@@ -525,6 +525,41 @@ def maxpool2x2(x):
     return y
 
 
+def conv2d_bwd(x, w_hwio, y, dy, leak=-1., need_dx=True):
+    """backward of conv2d (+ leaky relu when leak >= 0: `y` is the layer's output) -> (dx | None, dw [k,k,Cin,Cout], dbias)
+    [TF autodiff of app/modules.py:289-369 at main.py:357-358]"""
+    x, w_hwio, dy = _req(x, 'x', dim=4), _req(w_hwio, 'w', dim=4), _req(dy, 'dy', dim=4)
+    B, Cin, H, W = x.shape
+    k, _, _, Cout = w_hwio.shape
+    if tuple(dy.shape) != (B, Cout, H, W):
+        raise ValueError('conv2d_bwd: dy %s does not match output %s' % (tuple(dy.shape), (B, Cout, H, W)))
+    if leak >= 0.:
+        dy = leaky_relu_bwd(_req(y, 'y', dim=4), dy.clone(), leak)
+    lib = _lib.load()
+    dw = torch.empty_like(w_hwio)
+    db = torch.empty((Cout,), dtype=torch.float32, device=x.device)
+    _lib.check(lib.danet_conv2d_bwd_weights(_p(x), _p(dy), _p(dw), _p(db), B, Cin, Cout, H, W, k, _stream()), 'conv2d_bwd_weights')
+    _count()
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        _lib.check(lib.danet_conv2d_bwd_data(_p(dy), _p(w_hwio), _p(dx), B, Cin, Cout, H, W, k, _stream()), 'conv2d_bwd_data')
+        _count()
+    return dx, dw, db
+
+
+def maxpool2x2_bwd(x, dy):
+    """gradient of maxpool2x2 w.r.t. its input x [B,C,H,W] given dy [B,C,H/2,W/2]"""
+    x, dy = _req(x, 'x', dim=4), _req(dy, 'dy', dim=4)
+    B, Cn, H, W = x.shape
+    if tuple(dy.shape) != (B, Cn, H // 2, W // 2):
+        raise ValueError('maxpool2x2_bwd: dy %s does not match %s' % (tuple(dy.shape), (B, Cn, H // 2, W // 2)))
+    dx = torch.empty_like(x)
+    _lib.check(_lib.load().danet_maxpool2x2_bwd(_p(x), _p(dy), _p(dx), B * Cn, H, W, _stream()), 'maxpool2x2_bwd')
+    _count()
+    return dx
+
+
 def add(a, b):
     """a + b (the residual connection at app/modules.py:335)"""
     a = _req(a, 'a')

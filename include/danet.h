@@ -270,6 +270,17 @@ int danet_istft_fwd(const float* spec_c64, int n_sig, int T, float* wav, void* s
 int danet_conv2d_fwd(const float* x, const float* w_hwio, const float* bias, float* y, int B, int Cin, int Cout,
                      int H, int W, int ksize, float leak, void* stream);
 int danet_maxpool2x2_fwd(const float* x, float* y, long long n_img, int H, int W, void* stream);
+/* backward of the three layers above (TF autodiff of tf.layers.conv2d / max_pooling2d at main.py:357-358; the leaky
+ * ReLU's own derivative is danet_leaky_relu_bwd on the layer OUTPUT, applied to dy before these calls):
+ *   danet_conv2d_bwd_data     dx [B,Cin,H,W]  = dy [B,Cout,H,W] convolved with the flipped, channel-swapped kernel
+ *   danet_conv2d_bwd_weights  dw [k,k,Cin,Cout] = sum_{b,y,x} x[.., y+kh-r, x+kw-r] dy[.., y, x];  dbias [Cout] (nullable)
+ *   danet_maxpool2x2_bwd      dx [n_img,H,W]: each window's gradient goes to its first maximum; x is the pooling INPUT */
+int danet_conv2d_bwd_data(const float* dy, const float* w_hwio, float* dx, int B, int Cin, int Cout, int H, int W,
+                          int ksize, void* stream);
+int danet_conv2d_bwd_weights(const float* x, const float* dy, float* dw_hwio, float* dbias, int B, int Cin, int Cout,
+                             int H, int W, int ksize, void* stream);
+int danet_maxpool2x2_bwd(const float* x, const float* dy, float* dx, long long n_img, int H, int W, void* stream);
+
 int danet_add_fwd(const float* a, const float* b, float* out, long long n, void* stream);
 
 /* K4 fused (north star item 4): DotSeparatorSoftmax / DotSeparatorSigmoid (app/modules.py:548-603), the re-phasing

@@ -20,6 +20,7 @@ namespace danet {
 using namespace tc;
 
 constexpr int kTM = 128, kTN = 128, kTK = 64;
+constexpr int kMaxOrderedTiles = 64;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kTM * kTK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, B_hi, B_lo
@@ -96,6 +97,12 @@ struct GemmParams {
   int rows_per_mu;
   int kb_per_split;             // K blocks per blockIdx.z (split-K: partial sums are added atomically)
   int atomic;                   // 1 when gridDim.z > 1
+  // Pipelined hand-over to a consumer kernel that runs CONCURRENTLY (the recurrence that reads these input projections,
+  // danet_gemm_split_pipelined): row tile blockIdx.y is m_order[blockIdx.y] -- the tiles the consumer needs first come
+  // first -- and every epilogue warp bumps tile_flags[row tile] after its stores (release), so that
+  // tile_flags[m] == 4 * column tiles means "rows 128 m .. 128 m + 127 of C are complete and visible".
+  int* tile_flags;              // nullable
+  unsigned char m_order[kMaxOrderedTiles];
 };
 
 // Persistent over output tiles through CLUSTER LAUNCH CONTROL: the grid still has one CTA per tile, but a CTA that
@@ -180,7 +187,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(clc_empty_bar + slot, cph ^ 1);
         mbar_arrive_expect_tx(clc_full_bar + slot, 16);
         clc_try_cancel(smem_u32(clc_resp + 16 * slot), smem_u32(clc_full_bar + slot));
-        const int m0 = ty * kTM, n0 = tx * kTN, kb0 = tz * p.kb_per_split;
+        const int m0 = (p.tile_flags ? (int)p.m_order[ty] : ty) * kTM, n0 = tx * kTN, kb0 = tz * p.kb_per_split;
         const int nkb = min(p.kb_per_split, p.n_kblocks - kb0);
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
           const int s = kbc % kStages;
@@ -244,7 +251,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (uint32_t it = 0;; ++it) {
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
       const uint32_t tmem_acc = tmem_base + acc * kTN;
-      const int m0 = ty * kTM, n0 = tx * kTN;
+      const int tym = p.tile_flags ? (int)p.m_order[ty] : ty;
+      const int m0 = tym * kTM, n0 = tx * kTN;
       mbar_wait(tmem_full_bar + acc, aph);
       tc_fence_after();
       const int row = m0 + 32 * q + lane;
@@ -313,6 +321,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+      if (p.tile_flags) {
+        // this warp's 32 rows of the tile are stored: publish (every lane fences its own stores, one lane counts)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.tile_flags + tym, 1);
+      }
       const uint32_t slot = it % kClcSlots, cph = (it / kClcSlots) & 1;
       mbar_wait(clc_full_bar + slot, cph);
       const bool more = clc_query(smem_u32(clc_resp + 16 * slot), tx, ty, tz);
@@ -727,7 +741,8 @@ static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloa
 // the product on operands that are already split: A2 [2M, Kp], B2 [2N, Kp] bf16 (hi rows, then lo rows)
 int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float* bias, float* C, long long ldc,
                   int M, int N, int K, int out_perm_T, int accumulate, cudaStream_t stream, const float* row_mu = nullptr,
-                  const float* col_s = nullptr, int rows_per_mu = 1) {
+                  const float* col_s = nullptr, int rows_per_mu = 1, int* tile_flags = nullptr,
+                  const unsigned char* m_order = nullptr) {
   DANET_REQUIRE(aligned16(C) && (!bias || aligned16(bias)), DANET_E_ALIGN, "gemm: C and bias must be 16-byte aligned");
   DANET_REQUIRE(aligned16(A2) && aligned16(B2), DANET_E_ALIGN, "gemm: split operands must be 16-byte aligned");
   const int Kp = pad_k(K);
@@ -741,6 +756,8 @@ int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float*
   p.T = out_perm_T; p.nb = out_perm_T > 0 ? M / out_perm_T : 0;
   p.accumulate = accumulate;
   p.row_mu = row_mu; p.col_s = col_s; p.rows_per_mu = rows_per_mu > 0 ? rows_per_mu : 1;
+  p.tile_flags = tile_flags;
+  for (int i = 0; i < kMaxOrderedTiles; ++i) p.m_order[i] = m_order ? m_order[i] : (unsigned char)i;
   DANET_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
   dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
   DANET_REQUIRE(grid.y <= 65535, DANET_E_SHAPE, "gemm: M %d too large", M);
@@ -749,7 +766,7 @@ int gemm_tc_split(const __nv_bfloat16* A2, const __nv_bfloat16* B2, const float*
   {
     const int tiles = (int)(grid.x * grid.y), sms = num_sms();
     int splits = 1;
-    if (tiles * 4 <= sms * 3 && p.n_kblocks >= 16 && !row_mu) {
+    if (tiles * 4 <= sms * 3 && p.n_kblocks >= 16 && !row_mu && !tile_flags) {
       splits = (sms + tiles / 2) / tiles;
       const int max_splits = p.n_kblocks / 8;
       if (splits > max_splits) splits = max_splits;
@@ -923,4 +940,39 @@ extern "C" int danet_gemm_split(const void* A2, const void* B2, const float* bia
   if (M == 0) return DANET_OK;
   return gemm_tc_split(reinterpret_cast<const __nv_bfloat16*>(A2), reinterpret_cast<const __nv_bfloat16*>(B2), bias, C,
                        ldc, M, N, K, out_perm_T, accumulate ? 1 : 0, as_stream(stream), row_mu, col_s, rows_per_mu);
+}
+
+// Input projections of a recurrent layer, handed to the recurrence tile by tile (see GemmParams::tile_flags): same product
+// as danet_gemm_split with out_perm_T = T (rows b*T + t of A land at row t*B + b of C), the row tiles issued in the order
+// a forward AND a backward scan over time consume them (tiles holding the first / last frames of an utterance first), and
+// tile_flags[m] counting the finished (column tile, epilogue warp) pairs of row tile m.
+extern "C" int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M,
+                                          int N, int K, int T, int* tile_flags, int* flag_need, void* stream) {
+  DANET_REQUIRE(A2 && B2 && C && tile_flags && flag_need, DANET_E_ARG, "gemm_split_pipelined: null pointer");
+  DANET_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N && T >= 1 && M % T == 0, DANET_E_SHAPE,
+                "gemm_split_pipelined: M %d N %d K %d ldc %lld T %d", M, N, K, ldc, T);
+  const int mtiles = (M + kTM - 1) / kTM;
+  DANET_REQUIRE(mtiles <= kMaxOrderedTiles, DANET_E_SHAPE, "gemm_split_pipelined: %d row tiles (max %d, i.e. M <= %d)", mtiles,
+                kMaxOrderedTiles, kMaxOrderedTiles * kTM);
+  // key of a tile = the earliest scan step (from either end of time) that touches one of its rows
+  int key[kMaxOrderedTiles];
+  unsigned char order[kMaxOrderedTiles];
+  for (int m = 0; m < kMaxOrderedTiles; ++m) order[m] = (unsigned char)m;
+  for (int m = 0; m < mtiles; ++m) {
+    int best = T;
+    for (int r = m * kTM; r < (m + 1) * kTM && r < M; ++r) {
+      const int t = r % T, d = t < T - 1 - t ? t : T - 1 - t;
+      if (d < best) best = d;
+    }
+    key[m] = best;
+  }
+  for (int i = 1; i < mtiles; ++i) {            // stable insertion sort by key
+    const unsigned char v = order[i];
+    int j = i - 1;
+    while (j >= 0 && key[order[j]] > key[v]) { order[j + 1] = order[j]; --j; }
+    order[j + 1] = v;
+  }
+  *flag_need = 4 * ((N + kTN - 1) / kTN);
+  return gemm_tc_split(reinterpret_cast<const __nv_bfloat16*>(A2), reinterpret_cast<const __nv_bfloat16*>(B2), bias, C, ldc,
+                       M, N, K, T, 0, as_stream(stream), nullptr, nullptr, 1, tile_flags, order);
 }

@@ -55,6 +55,11 @@ struct LstmTcParams {
   long long pre_dir, pre_row;   // element strides of pre: address = dir*pre_dir + (t*B + b)*pre_row + gate*H + unit
   int n_dir, T, B, H;
   long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
+  // nullable: the input projections are still being PRODUCED while this kernel runs (danet_gemm_split_pipelined on another
+  // stream): row r = b*T + t of the producer's A operand belongs to row tile r / 128, complete once
+  // pre_flags[tile] >= flag_need.  A thread waits (acquire) the first time it needs a value of a tile.
+  const int* pre_flags;
+  int flag_need;
 };
 
 constexpr int kProfSlots = 16;
@@ -578,11 +583,23 @@ lstm_tc2_kernel(const LstmTcParams p) {
     // input projections are fetched kPreDepth steps ahead (they do not depend on the recurrence): under the stream-group
     // schedule the other groups' dense products load L2, and a fetch that is late stalls all ten CTAs of the cluster
     float pre_q[kPreDepth][4];
+    int tile_seen = -1;
     auto load_pre = [&](int s, float (&dst)[4]) {
 #pragma unroll
       for (int gg = 0; gg < 4; ++gg) dst[gg] = 0.f;
       if (valid && s < T) {
         const int to = dir ? T - 1 - s : s;
+        if (p.pre_flags) {
+          const int tile = (b * T + to) >> 7;
+          if (tile != tile_seen) {
+            int got;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.pre_flags + tile) : "memory");
+              if (got < p.flag_need) __nanosleep(100);
+            } while (got < p.flag_need);
+            tile_seen = tile;
+          }
+        }
         const float* qp = p.pre + (size_t)dir * p.pre_dir + ((size_t)to * B + b) * p.pre_row + unit;
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) dst[gg] = __ldcg(qp + gg * H);
@@ -833,7 +850,8 @@ int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H
 
 int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
                 const void* wh_packed, float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir,
-                int T, int B, int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                int T, int B, int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                const int* pre_flags, int flag_need) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
@@ -861,6 +879,7 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   }
   p.zero_pad = 0;
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
+  p.pre_flags = pre_flags; p.flag_need = flag_need;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
   const int clusters8 = n_dir * ((B + 7) / 8);
@@ -889,6 +908,9 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   bool pad_memset = false;
   const char* ver = getenv("DANET_LSTM_V");
   const bool gen1 = nb != 8 || (ver && atoi(ver) == 1 && !h_fp16);
+  DANET_REQUIRE(!pre_flags || !gen1, DANET_E_SHAPE,
+                "lstm_seq: the pipelined hand-over of the input projections needs the 8-utterances-per-cluster kernel "
+                "(B = %d is too large for co-resident clusters)", B);
   if (gen1) {
     if (out_split && out_kp > n_dir * H)
       DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,

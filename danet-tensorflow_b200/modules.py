@@ -110,6 +110,50 @@ class ToyEncoder(Encoder):
         K.colsum(dmid, out=g[n + '/linear0/B'])
 
 
+def _recurrent_layer_backward(model, rec, dx, bidir, need_dx, main, side):
+    """One (Bi)LSTM layer of the tape backwards: the BPTT kernel on the in-place gate gradients, then dX (critical path,
+    returned) and, on `side`, the stacked [I+H, 4H] weight gradient and the bias gradient of every direction -- followed by
+    the layer's bucket of the gradient exchange.  `dx` [B,T,n_dir*H] is the gradient of the layer's output."""
+    g, P = model.grads, model.params
+    H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
+    B, T = x.shape[0], x.shape[1]
+    names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if bidir else [rec['name']]
+    Ws = [P[n + '/LSTM/linear/W'] for n in names]
+    if side is not main:
+        # the clusters of the backward recurrence need whole SMs: queue them ahead of the side stream's tiles
+        hp_stream = model._priority_twin(main)
+        hp_stream.wait_stream(main)
+        with K.torch.cuda.stream(hp_stream):
+            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)           # [n_dir,T,B,4H]
+        main.wait_stream(hp_stream)
+    else:
+        da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)
+    x2 = x.reshape(B * T, I)
+    out2 = rec['out'].view(B * T, -1)
+    dx_prev = None
+    if need_dx:                                                                          # critical path first
+        dx_prev = K.torch.empty((B * T, I), dtype=K.torch.float32, device=x.device)
+        for d, n in enumerate(names):
+            K.gemm(da[d].view(T * B, 4 * H), Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
+        dx_prev = dx_prev.view(B, T, I)
+    side.wait_stream(main)                     # da is final (and, harmlessly, dX has been queued)
+    with K.torch.cuda.stream(side):
+        for d, n in enumerate(names):
+            da_d = da[d].view(T * B, 4 * H)
+            dW = g[n + '/LSTM/linear/W']
+            # ONE product for the stacked [I+H, 4H] gradient: A = [x ; h shifted by one step] paired
+            # time-major with da (sum_t X[b,t]^T da[t,b], sum_t h[b,t-+1]^T da[t,b]); each operand split once
+            a2 = K.split_operand_paired(x2, T, 0, rows_total=I + H)
+            K.split_operand_paired(out2[:, d * H:(d + 1) * H], T, -1 if d == 0 else 1, out=a2, row0=I,
+                                   rows_total=I + H)
+            b2 = K.split_operand(da_d, True)
+            K.gemm_split(a2, b2, I + H, 4 * H, T * B, out=dW)
+            K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
+        # this layer's gradients are queued: exchange them under the next layer's backward recurrence
+        model.grads_ready([n + sfx for n in names for sfx in ('/LSTM/linear/W', '/LSTM/linear/B')])
+    return dx_prev
+
+
 class _RecurrentEncoder(Encoder):
     N_LAYERS = 4
     HDIM = 300
@@ -171,41 +215,7 @@ class _RecurrentEncoder(Encoder):
             model.grads_ready([self.name + '/output/W'] + [k for k in g if k.endswith('/anchors')])
         dx = K.center(dx.view(B, T, odim))             # the gradient of x - mean(x) is the same centring
         for l in range(len(tape) - 2, -1, -1):
-            rec = tape[l]
-            H, x, I = rec['hdim'], rec['x'], rec['x'].shape[-1]
-            names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if self.BIDIR else [rec['name']]
-            Ws = [P[n + '/LSTM/linear/W'] for n in names]
-            if side is not main:
-                # the clusters of the backward recurrence need whole SMs: queue them ahead of the side stream's tiles
-                hp_stream = model._priority_twin(main)
-                hp_stream.wait_stream(main)
-                with K.torch.cuda.stream(hp_stream):
-                    da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)           # [n_dir,T,B,4H]
-                main.wait_stream(hp_stream)
-            else:
-                da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)
-            x2 = x.reshape(B * T, I)
-            out2 = rec['out'].view(B * T, -1)
-            if l > 0:                                                                            # critical path first
-                dx_prev = K.torch.empty((B * T, I), dtype=K.torch.float32, device=x.device)
-                for d, n in enumerate(names):
-                    K.gemm(da[d].view(T * B, 4 * H), Ws[d][:I], trans_b=True, out_perm_T=B, out=dx_prev, accumulate=d > 0)
-                dx = dx_prev.view(B, T, I)
-            side.wait_stream(main)                     # da is final (and, harmlessly, dX(l) has been queued)
-            with K.torch.cuda.stream(side):
-                for d, n in enumerate(names):
-                    da_d = da[d].view(T * B, 4 * H)
-                    dW = g[n + '/LSTM/linear/W']
-                    # ONE product for the stacked [I+H, 4H] gradient: A = [x ; h shifted by one step] paired
-                    # time-major with da (sum_t X[b,t]^T da[t,b], sum_t h[b,t-+1]^T da[t,b]); each operand split once
-                    a2 = K.split_operand_paired(x2, T, 0, rows_total=I + H)
-                    K.split_operand_paired(out2[:, d * H:(d + 1) * H], T, -1 if d == 0 else 1, out=a2, row0=I,
-                                           rows_total=I + H)
-                    b2 = K.split_operand(da_d, True)
-                    K.gemm_split(a2, b2, I + H, 4 * H, T * B, out=dW)
-                    K.colsum(da_d, out=g[n + '/LSTM/linear/B'])
-                # this layer's gradients are queued: exchange them under the next layer's backward recurrence
-                model.grads_ready([n + sfx for n in names for sfx in ('/LSTM/linear/W', '/LSTM/linear/B')])
+            dx = _recurrent_layer_backward(model, tape[l], dx, self.BIDIR, need_dx=l > 0, main=main, side=side)
         main.wait_stream(side)
 
 
@@ -236,7 +246,8 @@ class ConvBiLstmEncoder(Encoder):
     frames with a residual connection, two 3x3 convs whose 64 channels are un-pooled by depth-to-space, two 5x5 convs,
     and a bias-free dense layer FFT_SIZE -> F*E.  T must be a multiple of 4 (the reference pads, main.py:667-671).
     Variables are created under tf.layers' names (conv2d, conv2d_1, ..., dense) in the reference's order.
-    Inference only: no backward pass is provided for this encoder."""
+    Trains too: `backward` is the hand-derived adjoint of the whole stack, pinned by the reference's own tf.gradients
+    values (tests/golden/model_convbilstm_anchor_softmax.npz)."""
     TIME_ALIGN = 4             # two 2x2 max-pools over time: Model.separate pads waveforms to a multiple of 4 frames
 
     def _conv(self, idx, x, k, cout, init=None):
@@ -244,13 +255,14 @@ class ConvBiLstmEncoder(Encoder):
         nm = '%s/conv2d%s' % (self.name, '' if idx == 0 else '_%d' % idx)
         w = model.get_variable(nm + '/kernel', [k, k, x.shape[1], cout], init or _glorot_uniform_conv)
         b = model.get_variable(nm + '/bias', [cout], _zeros)
-        return K.conv2d(x, w, b, leak=hparams.RELU_LEAKAGE)
+        y = K.conv2d(x, w, b, leak=hparams.RELU_LEAKAGE)
+        if model._tape is not None:
+            self._saved['conv%d' % idx] = (nm, x, y)
+        return y
 
     def __call__(self, s_signals, s_dropout_keep=1.):
         _check_dropout(s_dropout_keep)
         model = self.model
-        if model._tape is not None:
-            raise NotImplementedError('conv-bilstm-v1 has no backward pass in this build (inference only)')
         B, T, F = s_signals.shape
         nfft, E = hparams.FFT_SIZE, hparams.EMBED_SIZE
         if T % 4 != 0:
@@ -259,6 +271,7 @@ class ConvBiLstmEncoder(Encoder):
             raise ValueError('conv-bilstm-v1: FEATURE_SIZE %d does not match FFT_SIZE %d' % (F, nfft))
         r = 2. / sqrt(nfft)
         w_init = _uniform(-r, r)
+        self._saved = {}
 
         def b_init(rs, shape):                                   # :280-285: [0 | input 1 | forget -1 | output 1]
             b = np.zeros(shape)
@@ -267,9 +280,11 @@ class ConvBiLstmEncoder(Encoder):
 
         x = s_signals.reshape(B, 1, T, F)
         m0 = self._conv(0, x, 5, 8)                                               # :289-293
-        m0 = K.maxpool2x2(self._conv(1, m0, 5, 16))                               # :294-300  [B,16,T/2,64]
+        p0_in = self._conv(1, m0, 5, 16)
+        m0 = K.maxpool2x2(p0_in)                                                  # :294-300  [B,16,T/2,64]
         m1 = self._conv(2, m0, 3, 32)
-        m1 = K.maxpool2x2(self._conv(3, m1, 3, 16))                               # :302-313  [B,16,T/4,32]
+        p1_in = self._conv(3, m1, 3, 16)
+        m1 = K.maxpool2x2(p1_in)                                                  # :302-313  [B,16,T/4,32]
         T4, F8 = m1.shape[2], m1.shape[3]
         m1 = K.center(m1.view(B, 16 * T4, F8)).view(B, 16, T4, F8)                # :315
         m2 = m1.permute(0, 2, 1, 3).reshape(B, T4, nfft * 2)                      # :318-320
@@ -286,9 +301,53 @@ class ConvBiLstmEncoder(Encoder):
         m5 = m5.permute(0, 2, 1, 3).reshape(B * T, nfft)                          # :371-373
         W = model.get_variable('%s/dense/kernel' % self.name, [nfft, F * E], _glorot_uniform)
         s_out = model.dense('%s/dense/kernel' % self.name, m5, W).view(B, T, F, E)                  # :375-379
+        if model._tape is not None:
+            self._saved.update(pool0_in=p0_in, pool1_in=p1_in, m5=m5, geom=(B, T, T4, F8))
+            model._tape.append(dict(conv=self._saved))
         if hparams.DEBUG:
             self.debug_fetches.update(conv_act=m1, lstm_act=m3, mid4=m4)
         return s_out
+
+    def backward(self, d_embed2, tape):
+        """d_embed2 [B*T, F*E] -> fills model.grads with what tf.gradients derives for this encoder (main.py:357-358):
+        dense layer, the four back-end convolutions through the depth-to-space shuffle, the residual sum and both
+        centrings, the two BiLSTM layers (BPTT kernels, as bilstm-orig), the two max-pools and the four front-end
+        convolutions.  The convolution gradients run on direct fp32 kernels (conv.cu)."""
+        model = self.model
+        g, P, name = model.grads, model.params, self.name
+        sv = tape[-1]['conv']
+        lstm = [rec for rec in tape if 'gates' in rec]
+        B, T, T4, F8 = sv['geom']
+        nfft = hparams.FFT_SIZE
+        leak = hparams.RELU_LEAKAGE
+        main = K.torch.cuda.current_stream()
+
+        def conv_bwd(idx, dy, need_dx=True):
+            nm, x, y = sv['conv%d' % idx]
+            dx, dw, db = K.conv2d_bwd(x, P[nm + '/kernel'], y, dy.contiguous(), leak=leak, need_dx=need_dx)
+            g[nm + '/kernel'].copy_(dw)
+            g[nm + '/bias'].copy_(db)
+            return dx
+
+        Wd = P[name + '/dense/kernel']
+        K.gemm(sv['m5'], d_embed2, trans_a=True, out=g[name + '/dense/kernel'])               # dW = m5^T dY
+        d5 = K.gemm(d_embed2, Wd, trans_b=True)                                              # [B*T, nfft]
+        d5 = d5.view(B, T // 2, 8, 2 * F8).permute(0, 2, 1, 3)                               # inverse of :371-373
+        d4 = conv_bwd(6, conv_bwd(7, d5))                                                    # [B,16,T/2,64]
+        d4 = d4.view(B, 16, T4, 2, F8, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, T4, F8)   # inverse of :354-357
+        d3 = conv_bwd(4, conv_bwd(5, d4))                                                    # [B,16,T/4,32]
+        d3 = K.center(d3.contiguous().view(B, 16 * T4, F8)).view(B, 16, T4, F8)              # :336 (self-adjoint)
+        d_m1 = d3                                                                            # residual branch (:335)
+        dx = d3.permute(0, 2, 1, 3).reshape(B, T4, 2 * nfft).contiguous()                    # inverse of :331-333
+        for l in (1, 0):
+            dx = _recurrent_layer_backward(model, lstm[l], dx, True, need_dx=True, main=main, side=main)
+        d_m1 = K.add(d_m1.contiguous(), dx.view(B, T4, 16, F8).permute(0, 2, 1, 3).contiguous())   # inverse of :318-320
+        d_m1 = K.center(d_m1.view(B, 16 * T4, F8)).view(B, 16, T4, F8)                       # :315
+        d = K.maxpool2x2_bwd(sv['pool1_in'], d_m1)
+        d = conv_bwd(2, conv_bwd(3, d))
+        d = K.maxpool2x2_bwd(sv['pool0_in'], d)
+        conv_bwd(0, conv_bwd(1, d), need_dx=False)
+        # (the convolution / dense gradients are exchanged by GradientBuckets.finish(): whatever no bucket covered)
 
 
 class _TruthEstimator(Estimator):

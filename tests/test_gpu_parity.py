@@ -196,6 +196,37 @@ def test_conv2d_maxpool_add(K, B, Cin, Cout, H, W, k):
     assert torch.equal(K.add(y, y).cpu(), (y + y).cpu())
 
 
+@pytest.mark.parametrize('B,Cin,Cout,H,W,k', [(2, 1, 8, 12, 129, 5), (1, 8, 16, 9, 64, 5), (3, 16, 32, 7, 33, 3),
+                                             (2, 32, 64, 5, 32, 3), (1, 3, 5, 4, 7, 1)])
+def test_conv2d_maxpool_backward(K, B, Cin, Cout, H, W, k):
+    """danet_conv2d_bwd_data / danet_conv2d_bwd_weights / danet_maxpool2x2_bwd (+ the leaky-ReLU derivative) against torch
+    autograd in float64 on the same layer (tf.layers.conv2d + max_pooling2d as the shim and the oracle restate them)"""
+    rs = np.random.RandomState(Cin * 10 + Cout)
+    x = rs.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (rs.standard_normal((k, k, Cin, Cout)) * .2).astype(np.float32)
+    b = rs.standard_normal(Cout).astype(np.float32)
+    dy = rs.standard_normal((B, Cout, H, W)).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True)
+    yt = torch.nn.functional.conv2d(xt, wt.permute(3, 2, 0, 1), bt, padding=k // 2)
+    yt = torch.maximum(yt * 0.3, yt)
+    (yt * torch.from_numpy(dy).double()).sum().backward()
+    xg, wg = cuda(x), cuda(w)
+    y = K.conv2d(xg, wg, cuda(b), leak=0.3)
+    dx, dw, db = K.conv2d_bwd(xg, wg, y, cuda(dy), leak=0.3)
+    assert rel(dx, xt.grad) < 2e-5
+    assert rel(dw, wt.grad) < 2e-5
+    assert rel(db, bt.grad) < 2e-5
+    assert K.conv2d_bwd(xg, wg, y, cuda(dy), leak=0.3, need_dx=False)[0] is None
+    if H >= 2 and W >= 2:
+        xp = torch.from_numpy(x).double().requires_grad_(True)
+        pooled = torch.nn.functional.max_pool2d(xp, 2, 2)
+        dp = rs.standard_normal(tuple(pooled.shape)).astype(np.float32)
+        (pooled * torch.from_numpy(dp).double()).sum().backward()
+        assert rel(K.maxpool2x2_bwd(xg, cuda(dp)), xp.grad) < 1e-6
+
+
 def test_split_operand_paired_weight_gradient(K):
     """danet_split_operand_paired + danet_gemm_split: dW = [x ; h shifted]^T da with the batch-major / time-major pairing
     of the tf.scan gradient (main.py:125-131, 357-358), against float64"""
@@ -611,8 +642,8 @@ def test_clip_adam(K):
 GRAD_FILES = [p for p in MODEL_FILES if 'lstm_tw' not in os.path.basename(p) or 'bilstm' in os.path.basename(p)]
 
 
-# conv-bilstm-v1 is an inference-only plugin in this build (its forward is pinned by test_model_forward_golden)
-TRAINABLE_FILES = [p for p in ALL_MODEL_FILES if 'convbilstm' not in os.path.basename(p)]
+# every registered encoder trains: conv-bilstm-v1's backward is pinned by the same reference-generated fixture as its forward
+TRAINABLE_FILES = list(ALL_MODEL_FILES)
 
 
 @pytest.mark.parametrize('path', TRAINABLE_FILES, ids=[os.path.basename(p)[6:-4] for p in TRAINABLE_FILES])

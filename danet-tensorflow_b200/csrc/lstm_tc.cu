@@ -592,11 +592,13 @@ lstm_tc2_kernel(const LstmTcParams p) {
         if (p.pre_flags) {
           const int tile = (b * T + to) >> 7;
           if (tile != tile_seen) {
+            // bounded (~2 s): a producer that never comes must end in a wrong answer, not in a hung device
             int got;
-            do {
+            for (int spin = 0; spin < (1 << 24); ++spin) {
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.pre_flags + tile) : "memory");
-              if (got < p.flag_need) __nanosleep(100);
-            } while (got < p.flag_need);
+              if (got >= p.flag_need) break;
+              __nanosleep(100);
+            }
             tile_seen = tile;
           }
         }

@@ -305,6 +305,43 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
     return (out, cell) if keep_cell else out
 
 
+PIPELINE_MAX_ROWS = 64 * 128
+
+
+def gemm_split_pipelined(a2, b2, m, n, k, T, flags, bias=None):
+    """gemm_split(out_perm_T=T) that publishes its row tiles through `flags` (int32[64], zeroed by the caller) in the order
+    a forward and a backward scan need them -> (C [m,n], flag_need)  [include/danet.h: danet_gemm_split_pipelined]"""
+    out = torch.empty((m, n), dtype=torch.float32, device=a2.device)
+    need = C.c_int(0)
+    _lib.check(_lib.load().danet_gemm_split_pipelined(_p(a2), _p(b2), _p(bias), _p(out), n, m, n, k, int(T), _p(flags),
+                                                      C.byref(need), _stream()), 'gemm_split_pipelined')
+    _count()
+    return out, need.value
+
+
+def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2, wh_packed=None):
+    """lstm_seq(interleaved=True, want_split=True) on input projections that are still being produced by
+    gemm_split_pipelined on another stream -> (hidden [B,T,n_dir*H], its split operand)"""
+    pre = _req(pre, 'pre', dim=4)
+    n_dir = len(w_list)
+    if tuple(pre.shape) != (T, B, n_dir, 4 * H):
+        raise ValueError('lstm_seq_pipelined: pre is %s, expected %s' % (tuple(pre.shape), (T, B, n_dir, 4 * H)))
+    ptrs = (C.c_void_p * n_dir)()
+    for d, w in enumerate(w_list):
+        w = _req(w, 'W[%d]' % d, dim=2)
+        ptrs[d] = w.data_ptr() + in_dim * 4 * H * 4
+    out = torch.empty((B, T, n_dir * H), dtype=torch.float32, device=pre.device)
+    kp = (n_dir * H + 63) // 64 * 64
+    out_split = torch.empty((2, B * T, kp), dtype=torch.bfloat16, device=pre.device)
+    lib = _lib.load()
+    ws = _ws(lib.danet_lstm_seq_workspace_bytes(n_dir, B, H), pre.device)
+    _lib.check(lib.danet_lstm_seq_fwd_pipelined(_p(pre), 4 * H, n_dir * 4 * H, ptrs, 4 * H, _p(wh_packed), _p(out),
+                                                _p(out_split), kp, n_dir, T, B, H, _p(flags), int(flag_need), _p(ws),
+                                                ws.numel(), int(backend), _stream()), 'lstm_seq_pipelined')
+    _count()
+    return out, out_split
+
+
 def split_operand(x, k_major_rows, out=None, row0=0, rows_total=None):
     """fp32 [rows,K] (k_major_rows=False) or [K,rows] (True) -> bf16 [2*rows_total, Kp] hi/lo operand"""
     x = _req_strided(x, 'x')

@@ -175,6 +175,7 @@ class Model(object):
         """C-ABI backend of the inference recurrence: 2 (fp16 state) unless switched off"""
         return 2 if self.RECURRENT_FP16 else 1
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
+    PIPELINE_INPUT_GEMM = True # the recurrence starts on the first finished tiles of its input projections
 
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
         """Same arithmetic as lyr_bilstm with the operand traffic trimmed: the two directions' input weights are
@@ -192,6 +193,32 @@ class Model(object):
         w2, bias2, wh_packed = ent
         prev = self._last_split
         a2 = prev[1] if prev is not None and prev[0] is s_x else K.split_operand(s_x.reshape(B * T, I), False)
+        backend = self.recurrent_backend()
+        if (self.PIPELINE_INPUT_GEMM and self.LSTM_PRIORITY_STREAM and B * T <= K.PIPELINE_MAX_ROWS
+                and B <= self.PIPELINE_GROUP and wh_packed is not None):
+            # The recurrence does not wait for the whole product: the GEMM issues its row tiles in the order the two scans
+            # consume them and publishes each through a flag; the recurrent kernel, launched from its high-priority stream
+            # as soon as the product has been QUEUED, spins on the flag of the tile it is about to read
+            # (danet_gemm_split_pipelined / danet_lstm_seq_fwd_pipelined).  ~40 of the product's ~50 us leave the group's
+            # critical path, four times per step.
+            cur = torch.cuda.current_stream()
+            hp_stream = self._priority_twin(cur)
+            flags = torch.zeros(64, dtype=torch.int32, device=s_x.device)
+            queued = cur.record_event()
+            pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * hdim, I, T, flags, bias=bias2)
+            pre = pre.view(T, B, 2, 4 * hdim)
+            if self._stagger_pending:
+                self._stagger_pending = False
+                self._stagger_event = cur.record_event()
+            K.stamp('%s gemm' % name)
+            hp_stream.wait_event(queued)
+            with torch.cuda.stream(hp_stream):
+                out, out_split = K.lstm_seq_pipelined(pre, [Wf, Wb], I, T, B, hdim, flags, need, backend=backend,
+                                                      wh_packed=wh_packed)
+            cur.wait_stream(hp_stream)
+            K.stamp('%s lstm' % name)
+            self._last_split = (out, out_split)
+            return out
         pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=T).view(T, B, 2, 4 * hdim)
         if self._stagger_pending:          # see separate(): the next stream group may start now
             self._stagger_pending = False
@@ -205,11 +232,11 @@ class Model(object):
             hp_stream.wait_stream(cur)
             with torch.cuda.stream(hp_stream):
                 out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
-                                            wh_packed=wh_packed, backend=self.recurrent_backend())
+                                            wh_packed=wh_packed, backend=backend)
             cur.wait_stream(hp_stream)
         else:
             out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
-                                        wh_packed=wh_packed, backend=self.recurrent_backend())
+                                        wh_packed=wh_packed, backend=backend)
         K.stamp('%s lstm' % name)
         self._last_split = (out, out_split)
         return out

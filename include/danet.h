@@ -135,6 +135,25 @@ int danet_gemm_split(const void* A2, const void* B2, const float* bias, const fl
                      const float* col_s, int rows_per_mu, float* C, long long ldc,
                      int M, int N, int K, int out_perm_T, int accumulate, void* stream);
 
+/* ---- K2a -> K2b hand-over: the recurrence starts while its input projections are still being computed ----------
+ * The reference runs `x W_x` inside every scan step (app/ops.py:139: a = [x_t, h] W); hoisted out of the scan it is one
+ * product per layer, but a product the recurrence has to wait for.  These two calls overlap them:
+ *   danet_gemm_split_pipelined  = danet_gemm_split(out_perm_T = T) with its 128-row tiles issued in the order a forward
+ *     AND a backward scan consume them (tiles holding the first / last frames of an utterance first) and
+ *     tile_flags[m] (int32[64], ZEROED BY THE CALLER before the call, on a stream the consumer is ordered after)
+ *     counting the finished (column tile, epilogue warp) pairs of row tile m; *flag_need receives the count that means
+ *     "rows 128 m .. 128 m + 127 of A, i.e. those (utterance, frame) pairs of C, are complete and visible".  M <= 8192.
+ *   danet_lstm_seq_fwd_pipelined = danet_lstm_seq_fwd_packed (inference outputs only) launched on ANOTHER stream without
+ *     waiting for the product: a thread spins (acquire) on the flag of the tile that holds the (utterance, frame) it is
+ *     about to read.  The producer never waits for the consumer, so any interleaving completes. */
+int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M, int N,
+                               int K, int T, int* tile_flags, int* flag_need, void* stream);
+int danet_lstm_seq_fwd_pipelined(const float* pre, long long pre_dir_stride, long long pre_row_stride,
+                                 const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
+                                 void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
+                                 const int* pre_flags, int flag_need, void* workspace, size_t workspace_bytes,
+                                 int backend, void* stream);
+
 /* ---- K2c + K3 fused: output projection with the anchor estimator's sums in its epilogue ----
  * replaces, in ONE kernel + a per-utterance finalize, the mean-centred bias-free output layer of the encoder
  * (app/modules.py:244-259: V = (x - mean_b(x)) W, reshaped [B,T,F,E]) AND AnchoredEstimator for two sources

@@ -837,3 +837,41 @@ def test_fused_inference_path_equals_unfused(D):
         K.attractor_anchor = raw
         D.Model.USE_FUSED_PROJ_ANCHOR = True
     assert float((fused - plain).abs().max() / plain.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize('B,T,I,backend', [(8, 501, 600, 2), (8, 501, 129, 1), (3, 40, 600, 2), (8, 1001, 600, 2)])
+def test_pipelined_input_projection_handover(K, B, T, I, backend):
+    """danet_gemm_split_pipelined + danet_lstm_seq_fwd_pipelined: the recurrence launched on a second stream BEFORE its input
+    projections exist, synchronised tile by tile through the flags, gives bit-identical results to product-then-recurrence"""
+    H = 300
+    rs = np.random.RandomState(T + I)
+    r = .75 / np.sqrt(H)
+    Ws = [cuda(rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32)) for _ in range(2)]
+    bias = cuda(np.concatenate([O.lstm_bias_init(H), O.lstm_bias_init(H)]).astype(np.float32))
+    x = cuda(rs.standard_normal((B * T, I)).astype(np.float32))
+    a2 = K.split_operand(x, False)
+    w2 = K.split_operand(Ws[0][:I], True, rows_total=8 * H, row0=0)
+    K.split_operand(Ws[1][:I], True, out=w2, rows_total=8 * H, row0=4 * H)
+    packed = K.lstm_pack_wh(Ws, I, H)
+    pre_ref = K.gemm_split(a2, w2, B * T, 8 * H, I, bias=bias, out_perm_T=T).view(T, B, 2, 4 * H)
+    out_ref, split_ref = K.lstm_seq(pre_ref, Ws, I, T, B, H, interleaved=True, want_split=True, wh_packed=packed,
+                                    backend=backend)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(priority=-1)
+    for rep in range(3):
+        cur = torch.cuda.current_stream()
+        flags = torch.zeros(64, dtype=torch.int32, device='cuda')
+        # make the consumer really start first: the producer's stream is held back by a long dummy kernel
+        queued = cur.record_event()
+        if rep:
+            torch.cuda._sleep(2000000)
+        pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * H, I, T, flags, bias=bias)
+        side.wait_event(queued)
+        with torch.cuda.stream(side):
+            out, split = K.lstm_seq_pipelined(pre.view(T, B, 2, 4 * H), Ws, I, T, B, H, flags, need, backend=backend,
+                                              wh_packed=packed)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        assert torch.equal(pre.view(T, B, 2, 4 * H), pre_ref)
+        assert int(flags[:(B * T + 127) // 128].min()) == need and int(flags[(B * T + 127) // 128:].max()) == 0
+        assert torch.equal(out, out_ref) and torch.equal(split, split_ref)

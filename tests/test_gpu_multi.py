@@ -46,8 +46,13 @@ for bucketed in (True, False):
     err = float((mean - gfull).abs().max()) / float(gfull.abs().max())
     assert err < 5e-5, (bucketed, err)          # bf16x3 products, shard vs full batch tiling
 m.apply_gradients(scale)
-perr = float((m._flat['param'] - full._flat['param']).abs().max())
-assert perr < 1e-6, perr
+# Adam's first step moves every weight by ~lr * sign(g): where the gradient is numerically zero the sign is noise, so the
+# parameters are compared where the gradient is significant (and bounded by 2 lr everywhere)
+diff = (m._flat['param'] - full._flat['param']).abs()
+sig = gfull.abs() > 1e-3 * gfull.abs().max()
+perr = float(diff[sig].max())
+assert perr < 2e-6, perr
+assert float(diff.max()) <= 2.1 * D.hparams.LR
 # every rank ends with bit-identical parameters (the exchanged gradient is the same everywhere)
 ref = m._flat['param'].clone()
 dist.broadcast(ref, 0)

@@ -306,9 +306,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps):
+    sm_khz = torch.cuda.get_device_properties(dev).clock_rate if hasattr(torch.cuda.get_device_properties(dev), 'clock_rate') else 1965000
+
+    def timed_loop(step_fn, steps, phase_ms=0.):
+        """K steps, CUDA events around each, max over ranks of the sum.  phase_ms > 0: this rank's first step starts that
+        much after the barrier (a device-side wait ahead of the first event), so that the ranks' steps -- equally long and
+        otherwise in lockstep -- end at different moments and their device-to-host bursts do not meet on the host side"""
         evs = []
         barrier()
+        if phase_ms > 0.:
+            torch.cuda._sleep(int(phase_ms * sm_khz))
         for _ in range(steps):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -335,7 +342,14 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev = timed_loop(step_dev, args.steps)
-    ms_e2e = timed_loop(step_e2e, args.steps)
+    ms_e2e_lockstep = timed_loop(step_e2e, args.steps)
+    if world > 1:
+        # N ranks of one box share the host side of their PCIe links: measured (tools/copy_contention.py) a rank's 8.2 MB of
+        # results take 152 us alone and 245 us when a second rank copies at the same moment.  Equal steps keep the ranks in
+        # lockstep, so every step ends in N simultaneous bursts; shifting rank r by r/N of a step interleaves them.
+        ms_e2e = timed_loop(step_e2e, args.steps, phase_ms=rank * (ms_dev / args.steps) / world)
+    else:
+        ms_e2e = ms_e2e_lockstep
     # the same K steps once more, eagerly on one stream, with CUDA events around every launch of the dominant
     # kernel (events cannot be read back from inside a replayed graph) and our launch counter running
     K.launches = 0
@@ -579,7 +593,10 @@ def main():
         'clocks': clocks, 'gpu_launches': launches // args.steps, 'gpu_launches_timed_region': launches,
         'cpu_baseline': cpu_baseline, 'roofline': roofline, 'parity': parity,
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
-                'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps,
+                'lockstep_value': total * args.steps / (ms_e2e_lockstep / 1e3),
+                'ranks': 'phase-shifted by rank/N of a step (their host-bound result copies interleave); lockstep_value = '
+                         'all ranks started together' if world > 1 else 'single rank'},
         # last on purpose: log tails keep the end of the line
         'train': train,
     }

@@ -356,8 +356,14 @@ def main():
     Timed.on = True
     ms_eager = timed_loop(lambda: model.separate(wav_dev, groups=1), args.steps)
     Timed.on = False
-    launches = K.launches
     per_kernel = {k: [a.elapsed_time(b) for a, b in v] for k, v in kernel_events.items()}
+    # our launches in one step of the TIMED schedule (4 stream groups; the graph replays exactly these): counted on one
+    # eager call of the same grouped step
+    K.launches = 0
+    model.separate(wav_dev)
+    torch.cuda.synchronize()
+    launches_per_step = K.launches
+    launches = launches_per_step * args.steps
     lstm_ms = per_kernel.get('lstm_seq', [])
     clocks = sampler.stop()
     got_e2e = out_host.clone()
@@ -485,9 +491,9 @@ def main():
     roofline = {'bound': 'tensor', 'kernel': 'lstm_seq (BiLSTM recurrence, one launch per layer)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': achieved / peak_tf if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 8-utterance launch (profiles/r01_ncu_v7_lstm.txt:
-                # 41.40 + 1.72 MB; the input projections stream in once, outputs stay in L2), scaled to this launch's batch
-                'traffic': 43.12e6 * B / 8.,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 8-utterance launch (profiles/r02_ncu_final_lstm.txt:
+                # 41.85 + 1.04 MB; the input projections stream in once, outputs stay in L2), scaled to this launch's batch
+                'traffic': 42.89e6 * B / 8.,
                 'traffic_source': 'ncu --set full, lstm_tc2_kernel<1>, 8 utterances per launch, scaled by B / 8',
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)'
                 if peaks else 'fallback',
@@ -590,7 +596,7 @@ def main():
                       ('; the recurrent product takes h_{t-1} as one fp16 value x fp16 hi/lo weights' if fp16_on else ''),
         'backend': K.DEFAULT_BACKEND, 'cuda_graph': bool(args.graph),
         'kernels': kernels, 'other_configs': other, 'precision_ab': precision_ab,
-        'clocks': clocks, 'gpu_launches': launches // args.steps, 'gpu_launches_timed_region': launches,
+        'clocks': clocks, 'gpu_launches': launches, 'gpu_launches_per_step': launches_per_step,
         'cpu_baseline': cpu_baseline, 'roofline': roofline, 'parity': parity,
         'e2e': {'value': e2e, 'unit': 'mixtures/s', 'h2d_bytes_per_step': int(wav_host.numel() * 4),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps,

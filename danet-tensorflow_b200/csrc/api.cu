@@ -90,3 +90,12 @@ extern "C" unsigned int danet_crc32c(const void* data, size_t n, unsigned int cr
   while (n--) crc = tab[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
   return ~crc;
 }
+
+// cudaMemsetAsync behind the C-ABI: a memset NODE when the stream is being captured, no kernel launch (the completion
+// flags of danet_gemm_split_pipelined are cleared with it)
+extern "C" int danet_zero_async(void* ptr, size_t bytes, void* stream) {
+  DANET_REQUIRE(ptr || bytes == 0, DANET_E_ARG, "zero_async: null pointer");
+  if (bytes == 0) return DANET_OK;
+  DANET_CUDA(cudaMemsetAsync(ptr, 0, bytes, danet::as_stream(stream)));
+  return DANET_OK;
+}

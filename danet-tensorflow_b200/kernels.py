@@ -308,6 +308,13 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
 PIPELINE_MAX_ROWS = 64 * 128
 
 
+def pipeline_flags(device):
+    """the 64 completion flags of gemm_split_pipelined, cleared on the current stream (memset, not a kernel)"""
+    flags = torch.empty(64, dtype=torch.int32, device=device)
+    _lib.check(_lib.load().danet_zero_async(_p(flags), 256, _stream()), 'zero_async')
+    return flags
+
+
 def gemm_split_pipelined(a2, b2, m, n, k, T, flags, bias=None):
     """gemm_split(out_perm_T=T) that publishes its row tiles through `flags` (int32[64], zeroed by the caller) in the order
     a forward and a backward scan need them -> (C [m,n], flag_need)  [include/danet.h: danet_gemm_split_pipelined]"""

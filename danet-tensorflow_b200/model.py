@@ -208,7 +208,7 @@ class Model(object):
             # critical path, four times per step.
             cur = torch.cuda.current_stream()
             hp_stream = self._priority_twin(cur)
-            flags = torch.zeros(64, dtype=torch.int32, device=s_x.device)
+            flags = K.pipeline_flags(s_x.device)
             queued = cur.record_event()
             pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * hdim, I, T, flags, bias=bias2)
             pre = pre.view(T, B, 2, 4 * hdim)

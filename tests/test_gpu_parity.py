@@ -863,7 +863,7 @@ def test_pipelined_input_projection_handover(K, B, T, I, backend):
     side = torch.cuda.Stream(priority=-1)
     for rep in range(3):
         cur = torch.cuda.current_stream()
-        flags = torch.zeros(64, dtype=torch.int32, device='cuda')
+        flags = K.pipeline_flags('cuda')
         # make the consumer really start first: the producer's stream is held back by a long dummy kernel
         queued = cur.record_event()
         if rep:

@@ -91,11 +91,24 @@ extern "C" unsigned int danet_crc32c(const void* data, size_t n, unsigned int cr
   return ~crc;
 }
 
-// cudaMemsetAsync behind the C-ABI: a memset NODE when the stream is being captured, no kernel launch (the completion
-// flags of danet_gemm_split_pipelined are cleared with it)
+// Clears a small buffer (the completion flags of danet_gemm_split_pipelined) with a one-block KERNEL: inside a captured
+// graph a cudaMemsetAsync becomes a memset node, and sixteen of those per step measured 30 us slower than sixteen tiny
+// kernels (2.424 vs 2.394 ms per step, profiles/r02_ab_switches.txt).
+namespace danet {
+__global__ void zero_words_kernel(unsigned int* p, size_t n) {
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
+}
+}  // namespace danet
+
 extern "C" int danet_zero_async(void* ptr, size_t bytes, void* stream) {
   DANET_REQUIRE(ptr || bytes == 0, DANET_E_ARG, "zero_async: null pointer");
   if (bytes == 0) return DANET_OK;
-  DANET_CUDA(cudaMemsetAsync(ptr, 0, bytes, danet::as_stream(stream)));
+  DANET_REQUIRE(bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 3) == 0, DANET_E_ALIGN, "zero_async: 4-byte granularity");
+  if (bytes <= 64 * 1024) {
+    danet::zero_words_kernel<<<1, 256, 0, danet::as_stream(stream)>>>(reinterpret_cast<unsigned int*>(ptr), bytes / 4);
+    DANET_LAUNCH_CHECK();
+  } else {
+    DANET_CUDA(cudaMemsetAsync(ptr, 0, bytes, danet::as_stream(stream)));
+  }
   return DANET_OK;
 }

@@ -309,9 +309,10 @@ PIPELINE_MAX_ROWS = 64 * 128
 
 
 def pipeline_flags(device):
-    """the 64 completion flags of gemm_split_pipelined, cleared on the current stream (memset, not a kernel)"""
+    """the 64 completion flags of gemm_split_pipelined, cleared on the current stream (danet_zero_async)"""
     flags = torch.empty(64, dtype=torch.int32, device=device)
     _lib.check(_lib.load().danet_zero_async(_p(flags), 256, _stream()), 'zero_async')
+    _count()
     return flags
 
 

@@ -208,8 +208,13 @@ class Model(object):
             # critical path, four times per step.
             cur = torch.cuda.current_stream()
             hp_stream = self._priority_twin(cur)
-            flags = K.pipeline_flags(s_x.device)
+            flags = (K.pipeline_flags(s_x.device) if self.FLAGS_BY_MEMSET
+                     else torch.zeros(64, dtype=torch.int32, device=s_x.device))
             queued = cur.record_event()
+            if self.LSTM_HEADSTART_US > 0:
+                # give the recurrence's 10-CTA clusters first pick of the SMs: launched at the same moment, the product's
+                # single CTAs fill SMs one by one and a cluster never finds ten free ones in a GPC until the product drains
+                torch.cuda._sleep(int(self.LSTM_HEADSTART_US * 1840))
             pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * hdim, I, T, flags, bias=bias2)
             pre = pre.view(T, B, 2, 4 * hdim)
             if self._stagger_pending:
@@ -557,6 +562,8 @@ class Model(object):
         self._packed_ready = True
 
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
+    LSTM_HEADSTART_US = 0   # experiment: delay the pipelined product by this much so the recurrent clusters are placed first
+    FLAGS_BY_MEMSET = True  # completion flags cleared through the C-ABI (danet_zero_async) instead of a torch fill kernel
     STAGGER_US = 0          # experiment: release the next group this long after the first product starts (0 = when it ends)
     PREFETCH_H2D = True     # pinned host input: the groups' slices are copied in order by one copy stream
     PIPELINE_MAX_GROUPS = 4

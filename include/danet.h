@@ -146,7 +146,8 @@ int danet_gemm_split(const void* A2, const void* B2, const float* bias, const fl
  *   danet_lstm_seq_fwd_pipelined = danet_lstm_seq_fwd_packed (inference outputs only) launched on ANOTHER stream without
  *     waiting for the product: a thread spins (acquire) on the flag of the tile that holds the (utterance, frame) it is
  *     about to read.  The producer never waits for the consumer, so any interleaving completes. */
-/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (a memset node under stream capture): clears tile_flags */
+/* zero `bytes` (multiple of 4) at ptr on `stream`; small buffers by a one-block kernel (cheaper than a memset node inside a
+ * captured graph): clears tile_flags */
 int danet_zero_async(void* ptr, size_t bytes, void* stream);
 int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M, int N,
                                int K, int T, int* tile_flags, int* flag_need, void* stream);

@@ -308,10 +308,11 @@ def lstm_seq(pre, w_list, in_dim, T, B, H, backend=None, keep_cell=False, keep_g
 PIPELINE_MAX_ROWS = 64 * 128
 
 
-def pipeline_flags(device):
-    """the 64 completion flags of gemm_split_pipelined, cleared on the current stream (danet_zero_async)"""
-    flags = torch.empty(64, dtype=torch.int32, device=device)
-    _lib.check(_lib.load().danet_zero_async(_p(flags), 256, _stream()), 'zero_async')
+def pipeline_flags(device, sets=None):
+    """the 64 completion flags of gemm_split_pipelined (or `sets` x 64 of them), cleared on the current stream
+    (danet_zero_async)"""
+    flags = torch.empty((64,) if sets is None else (int(sets), 64), dtype=torch.int32, device=device)
+    _lib.check(_lib.load().danet_zero_async(_p(flags), flags.numel() * 4, _stream()), 'zero_async')
     _count()
     return flags
 

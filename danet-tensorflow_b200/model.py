@@ -42,6 +42,7 @@ class Model(object):
         self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
         self._ar_events = []
         self._vars_ready = False          # every variable exists (created in the reference's order)
+        self._flag_pool = None            # [tensor [FLAG_SETS, 64] int32 cleared for the running group, sets handed out]
         self._fuse_anchor = None          # inference: anchors handed to the encoder's projection (fused estimator sums)
         self._fused_attrs = None          # (embedding, attractors) the fused projection produced
         self.step_count = 0
@@ -182,6 +183,18 @@ class Model(object):
     # with it (first convolution's kernel: 3.3e-3 -- the max-pools turn the 1e-4 forward deviation into routing changes).
     TRAIN_RECURRENT_FP16 = False
 
+    FLAG_SETS = 8              # completion-flag sets cleared by ONE launch per group and step (one set per recurrent layer)
+
+    def _next_flags(self, device):
+        """64 cleared completion flags for one pipelined product.  `separate` clears FLAG_SETS sets with a single launch
+        when a group starts (off the per-layer critical path) and the layers take them in turn; outside that (or when
+        the pool is used up) a set is cleared on the spot."""
+        pool = self._flag_pool
+        if pool is not None and pool[1] < self.FLAG_SETS:
+            pool[1] += 1
+            return pool[0][pool[1] - 1]
+        return K.pipeline_flags(device)
+
     def _lyr_bilstm_packed(self, name, s_x, hdim, weights):
         """Same arithmetic as lyr_bilstm with the operand traffic trimmed: the two directions' input weights are
         split to bf16 hi/lo ONCE and kept side by side (one product, N = 8H, instead of two), and the layer input
@@ -208,8 +221,7 @@ class Model(object):
             # critical path, four times per step.
             cur = torch.cuda.current_stream()
             hp_stream = self._priority_twin(cur)
-            flags = (K.pipeline_flags(s_x.device) if self.FLAGS_BY_MEMSET
-                     else torch.zeros(64, dtype=torch.int32, device=s_x.device))
+            flags = self._next_flags(s_x.device)
             queued = cur.record_event()
             if self.LSTM_HEADSTART_US > 0:
                 # give the recurrence's 10-CTA clusters first pick of the SMs: launched at the same moment, the product's
@@ -563,7 +575,6 @@ class Model(object):
 
     PIPELINE_GROUP = 8      # utterances per stream group = one recurrent cluster's batch tile
     LSTM_HEADSTART_US = 0   # experiment: delay the pipelined product by this much so the recurrent clusters are placed first
-    FLAGS_BY_MEMSET = True  # completion flags cleared through the C-ABI (danet_zero_async) instead of a torch fill kernel
     STAGGER_US = 0          # experiment: release the next group this long after the first product starts (0 = when it ends)
     PREFETCH_H2D = True     # pinned host input: the groups' slices are copied in order by one copy stream
     PIPELINE_MAX_GROUPS = 4
@@ -602,6 +613,7 @@ class Model(object):
 
         def run(lo, hi, w=None):
             K.stamp('g%d start' % lo)
+            self._flag_pool = [K.pipeline_flags(self.device, self.FLAG_SETS), 0] if self.PIPELINE_INPUT_GEMM else None
             if w is None:
                 w = wav[lo:hi]
                 if not w.is_cuda:
@@ -623,6 +635,7 @@ class Model(object):
                 else:
                     out[lo:hi].copy_(K.istft(sep), non_blocking=True)
             K.stamp('g%d end' % lo)
+            self._flag_pool = None
 
         if groups <= 1:
             run(0, B)

@@ -592,12 +592,19 @@ lstm_tc2_kernel(const LstmTcParams p) {
         if (p.pre_flags) {
           const int tile = (b * T + to) >> 7;
           if (tile != tile_seen) {
-            // bounded (~2 s): a producer that never comes must end in a wrong answer, not in a hung device
-            int got;
+            // bounded (~2 s): a producer that never comes must not hang the device -- the values of that tile are then
+            // replaced by NaN, which the recurrence carries into every later output of the utterance (a visibly invalid
+            // result instead of a silently wrong one)
+            int got = 0;
             for (int spin = 0; spin < (1 << 24); ++spin) {
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.pre_flags + tile) : "memory");
               if (got >= p.flag_need) break;
               __nanosleep(100);
+            }
+            if (got < p.flag_need) {
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) dst[gg] = __int_as_float(0x7fc00000);
+              return;
             }
             tile_seen = tile;
           }

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_r.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_r.log

@@ -20,6 +20,14 @@ size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
 size_t lstm_tc_pack_bytes(int n_dir, int H);
 int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed, cudaStream_t stream);
 bool lstm_tc_supported(int H);
+// 384 < H <= 608 (lstm_wide_tc.cu): groups of ceil(H/32) CTAs exchanging h through L2, backend 2 only
+bool lstm_wide_supported(int H);
+size_t lstm_wide_workspace_bytes(int n_dir, int B, int H);
+size_t lstm_wide_pack_bytes(int n_dir, int H);
+int lstm_wide_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed, cudaStream_t stream);
+int lstm_wide_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
+                  const void* wh_packed, float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp,
+                  int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 constexpr int kU = 8;      // hidden units per CTA
 constexpr int kBt = 16;    // utterances per CTA
@@ -167,11 +175,14 @@ extern "C" size_t danet_lstm_seq_workspace_bytes(int n_dir, int B, int H) {
   if (n_dir < 1 || B < 1 || H < 1) return 256;
   size_t simt = (((size_t)n_dir * ((B + kBt - 1) / kBt) * sizeof(int)) + 255) / 256 * 256;
   size_t tc = lstm_tc_workspace_bytes(n_dir, B, H);
+  if (H % 4 == 0 && lstm_wide_supported(H)) tc = lstm_wide_workspace_bytes(n_dir, B, H);
   return simt > tc ? simt : tc;
 }
 
 extern "C" size_t danet_lstm_pack_wh_bytes(int n_dir, int H) {
-  if (n_dir < 1 || H < 4 || !lstm_tc_supported(H)) return 0;
+  if (n_dir < 1 || H < 4) return 0;
+  if (lstm_wide_supported(H)) return lstm_wide_pack_bytes(n_dir, H);
+  if (!lstm_tc_supported(H)) return 0;
   return lstm_tc_pack_bytes(n_dir, H);
 }
 
@@ -181,6 +192,11 @@ extern "C" int danet_lstm_pack_wh(const float* const* host_Wh, long long ldw, in
   DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_pack_wh: n_dir %d", n_dir);
   for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_pack_wh: null Wh[%d]", d);
   DANET_REQUIRE(H >= 4 && H % 4 == 0 && ldw >= 4ll * H, DANET_E_SHAPE, "lstm_pack_wh: H %d ldw %lld", H, ldw);
+  if (lstm_wide_supported(H)) {
+    DANET_REQUIRE(packed_bytes >= lstm_wide_pack_bytes(n_dir, H), DANET_E_WORKSPACE, "lstm_pack_wh: buffer %zu < %zu",
+                  packed_bytes, lstm_wide_pack_bytes(n_dir, H));
+    return lstm_wide_pack_wh(host_Wh, ldw, n_dir, H, packed, as_stream(stream));
+  }
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE, "lstm_pack_wh: H %d is outside the tcgen05 backend's range", H);
   DANET_REQUIRE(packed_bytes >= lstm_tc_pack_bytes(n_dir, H), DANET_E_WORKSPACE, "lstm_pack_wh: buffer %zu < %zu",
                 packed_bytes, lstm_tc_pack_bytes(n_dir, H));
@@ -249,6 +265,11 @@ static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long lo
                 danet_lstm_seq_workspace_bytes(n_dir, B, H));
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
+  if (backend == 2 && lstm_wide_supported(H)) {
+    DANET_REQUIRE(!pre_flags, DANET_E_SHAPE, "lstm_seq: the pipelined hand-over needs H <= 384 (got %d)", H);
+    return lstm_wide_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, cell_seq, gates_seq, out_split,
+                         out_split_kp, n_dir, T, B, H, workspace, workspace_bytes, st);
+  }
   if (backend >= 1)
     return lstm_tc_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, cell_seq, gates_seq, out_split, out_split_kp,
                        n_dir, T, B, H, backend == 2, workspace, workspace_bytes, st, pre_flags, flag_need);

@@ -18,6 +18,9 @@ FFT_STRIDE = 64
 DEFAULT_BACKEND = int(os.environ.get('DANET_BACKEND', '1'))
 
 TC_LSTM_MAX_H = 384
+# 384 < H <= 608 (the `lstm-orig` encoder): backend 2 runs the wide tcgen05 kernel (csrc/lstm_wide_tc.cu: groups of
+# ceil(H/32) CTAs exchanging h through L2); backend 1 has no kernel there, backend 0 is the exact fp32 one
+TC_WIDE_MAX_H = 608
 
 # launch counter: bench.py reports how many of OUR kernels ran inside the timed region
 launches = 0

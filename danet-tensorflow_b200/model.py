@@ -142,6 +142,12 @@ class Model(object):
             out, cell = K.lstm_seq(pre, [W], I, T, B, hdim, keep_cell=True, keep_gates=True)
             self._tape.append(dict(name=name, x=s_x, gates=pre, cell=cell, out=out, hdim=hdim))
             return out
+        if (self.RECURRENT_FP16 and K.DEFAULT_BACKEND == 1 and K.TC_LSTM_MAX_H < hdim <= K.TC_WIDE_MAX_H):
+            # lstm-orig (H = 600) in inference: the wide tcgen05 kernel on a cached weight image (fp16 state, C-ABI backend 2)
+            wh_packed = self._packed.get(name + '/wh')
+            if wh_packed is None:
+                wh_packed = self._packed[name + '/wh'] = K.lstm_pack_wh([W], I, hdim)
+            return K.lstm_seq(pre, [W], I, T, B, hdim, backend=2, wh_packed=wh_packed)
         return K.lstm_seq(pre, [W], I, T, B, hdim)
 
     def lyr_bilstm(self, name, s_x, hdim, w_init=None, b_init=None):
@@ -603,9 +609,11 @@ class Model(object):
         if groups is None:
             groups = max(1, min(self.PIPELINE_MAX_GROUPS, B // self.PIPELINE_GROUP))
             geo = getattr(self.encoder, '_geometry', None)
-            if geo is not None and geo()[1] > K.TC_LSTM_MAX_H:
-                # H too large for the cluster kernel (lstm-orig, H = 600): the fp32 cooperative kernel needs all its CTAs
-                # resident, so more than two groups only queue behind each other (measured 45.8 ms with 4, 31.6 with 2)
+            if geo is not None and geo()[1] > K.TC_LSTM_MAX_H and not (
+                    self.RECURRENT_FP16 and K.DEFAULT_BACKEND == 1 and geo()[1] <= K.TC_WIDE_MAX_H):
+                # H too large for the tcgen05 kernels (or they are switched off): the fp32 cooperative kernel needs all
+                # its CTAs resident, so more than two groups only queue behind each other (lstm-orig, H = 600: measured
+                # 45.8 ms with 4, 31.6 with 2).  The wide tcgen05 kernel takes 19 SMs per group of 8: four groups fit.
                 groups = min(groups, 2)
         Cn, T = hparams.MAX_N_SIGNAL, K.num_frames(n)
         if out is None:

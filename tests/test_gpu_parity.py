@@ -265,8 +265,8 @@ def test_lstm_seq(K, backend, n_dir, B, T, I, H):
     xg = cuda(x).reshape(B * T, I)
     pre = torch.empty(n_dir, T, B, 4 * H, device='cuda')
     Wg = [cuda(w) for w in Ws]
-    if backend >= 1 and H > K.TC_LSTM_MAX_H:
-        with pytest.raises(ValueError):      # documented limit of the cluster-resident kernel
+    if backend == 1 and H > K.TC_LSTM_MAX_H:
+        with pytest.raises(ValueError):      # documented limit of the cluster-resident kernel (backend 2: the wide kernel)
             K.lstm_seq(pre, Wg, I, T, B, H, backend=backend)
         return
     for d in range(n_dir):
@@ -311,7 +311,50 @@ def test_lstm_seq_packed_weights(K, backend, n_dir, B, T, H):
     assert rel((hi + lo)[:, :n_dir * H], a.reshape(B * T, n_dir * H)) < 1e-5
     if kp > n_dir * H:
         assert float(b_split[:, :, n_dir * H:].abs().max()) == 0.
-    assert K.lstm_pack_wh([w for w in Wg], I, 600) is None        # outside the cluster kernel's range
+    assert K.lstm_pack_wh([w for w in Wg], I, 640) is None        # outside both tcgen05 kernels' range
+
+
+@pytest.mark.parametrize('n_dir,B,T,I,H', [(1, 8, 64, 129, 600), (1, 32, 501, 600, 600), (2, 11, 37, 64, 416),
+                                           (1, 1, 5, 129, 608), (1, 57, 12, 40, 600)])
+def test_lstm_seq_wide(K, n_dir, B, T, I, H):
+    """384 < H <= 608 on tcgen05 (csrc/lstm_wide_tc.cu, C-ABI backend 2: the `lstm-orig` encoder's layers,
+    app/modules.py:140-196): groups of ceil(H/32) CTAs, Wh hi image + part of the lo image in tensor memory, the rest of
+    lo in shared memory, h exchanged through L2.  Against the float64 oracle AND the exact-fp32 kernel; packed image
+    == on-the-fly image; the emitted operand is the hidden sequence; B = 57 needs two cooperative launches."""
+    rs = np.random.RandomState(B * T + H)
+    r = 1.15 / np.sqrt(H)
+    x = rs.standard_normal((B, T, I)).astype(np.float32)
+    Ws = [rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32) for _ in range(n_dir)]
+    Bs = [O.lstm_bias_init(H).astype(np.float32) + 0.1 * rs.standard_normal(4 * H).astype(np.float32)
+          for _ in range(n_dir)]
+    xg = cuda(x).reshape(B * T, I)
+    pre = torch.empty(n_dir, T, B, 4 * H, device='cuda')
+    Wg = [cuda(w) for w in Ws]
+    for d in range(n_dir):
+        K.linear(xg, Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
+    packed = K.lstm_pack_wh(Wg, I, H)
+    assert packed is not None
+    out, cell, split = K.lstm_seq(pre, Wg, I, T, B, H, backend=2, keep_cell=True, want_split=True, wh_packed=packed)
+    assert bool(torch.isfinite(out).all())
+    exact = K.lstm_seq(pre, Wg, I, T, B, H, backend=0)
+    assert rel(out, exact) < 5e-4
+    if B * T <= 2048:
+        xt = torch.from_numpy(x).double()
+        refs = [O.lstm_layer(xt, torch.from_numpy(Ws[0]).double(), torch.from_numpy(Bs[0]).double())]
+        if n_dir == 2:
+            refs.append(torch.flip(O.lstm_layer(torch.flip(xt, [1]), torch.from_numpy(Ws[1]).double(),
+                                                torch.from_numpy(Bs[1]).double()), [1]))
+        assert rel(out, torch.cat(refs, -1)) < 5e-4
+    assert cell.shape == (n_dir, T, B, H) and bool(torch.isfinite(cell).all())
+    assert torch.equal(K.lstm_seq(pre, Wg, I, T, B, H, backend=2), out)          # image packed on the fly by the library
+    Wz = [w.clone() for w in Wg]
+    for w in Wz:
+        w[I:].zero_()
+    assert torch.equal(K.lstm_seq(pre, Wz, I, T, B, H, backend=2, wh_packed=packed), out)   # the image is what is read
+    hi, lo = split[0].float(), split[1].float()
+    assert rel((hi + lo)[:, :n_dir * H], out.reshape(B * T, n_dir * H)) < 1e-5
+    if split.shape[-1] > n_dir * H:
+        assert float(split[:, :, n_dir * H:].abs().max()) == 0.
 
 
 # ---------------------------------------------------------------- K3: attractors

@@ -19,6 +19,11 @@
 //     words it needs with 16-byte volatile loads and writes the payload straight into the UMMA B operand.  One L2 round
 //     trip per step instead of store -> fence -> flag -> poll -> load.  Two buffers by step parity; a word of step s+2
 //     can only be written after its producer has consumed every slice of step s+1, whose producers had consumed step s;
+//     Measured and dropped: completing the gather in chunks of four producers with a barrier per chunk so that the MMAs
+//     of a chunk start early (955 -> 1145 us per layer: five proxy fences + arrivals per thread cost more than the
+//     overlap returns), delaying the first poll by 150-600 cycles (no change: the gather is bound by the ~64 B/cycle an
+//     SM pulls from L2 and by the skew between the CTAs, not by a poll that leaves a moment too early), all fp16 MMAs
+//     before all fp8 MMAs (+140 cycles against interleaving them);
 //   * the CTAs of a group spin on each other, so the grid is launched cooperatively (co-residency) and every spin is
 //     bounded: a peer that never comes poisons the result with NaN instead of hanging the device.
 // Everything else (activation math, output layouts, the emitted bf16 hi/lo operand of the next layer) is the epilogue

@@ -144,6 +144,26 @@ def test_cfg2_three_layer_variant(D, fp16):
     _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, B, '3x600 fp16 %d' % fp16)
 
 
+def test_cfg2_lstm_orig_encoder(D):
+    """`lstm-orig` (app/modules.py:140-196: 4 x 600 unidirectional) at the cfg 2 shape on the wide tcgen05 recurrent kernel
+    (fp16 state, residual weights as fp8): every tensor against the float64 oracle, and against the exact-fp32 kernel"""
+    import bench
+    B, n_ref = 8, 2
+    _configure(D, 1, True, BATCH_SIZE=B, ENCODER_TYPE='lstm-orig')
+    wav_np = bench.synth_mixtures(B, bench.N_SAMPLES, 4242)
+    P = O.reference_init(1337, encoder='lstm-orig', estimators=('infer_estimator',), dtype=torch.float64)
+    ref_wav, ref_sig, aux = O.separate_waveforms(wav_np[:n_ref], P, encoder='lstm-orig', dtype=torch.float64)
+    model = D.Model('full-lstm-orig').build()
+    model.load_params({k.replace('infer_estimator', 'train_estimator'): v for k, v in P.items()})
+    wav = torch.from_numpy(wav_np).cuda()
+    got = _product_stages(D, model, wav)
+    assert got['embed'].shape == (B, 501, 129, 20)
+    _check_against_oracle(got, model.separate(wav), ref_wav, ref_sig, aux, n_ref, 'lstm-orig wide tcgen05')
+    D.Model.RECURRENT_FP16 = False                       # H = 600 then runs the exact-fp32 cooperative kernel
+    exact = _product_stages(D, model, wav)
+    assert rel(got['embed'], exact['embed']) < TOL and absdiff(got['masks'], exact['masks']) < TOL
+
+
 @pytest.mark.parametrize('est', ['anchor', 'kmeans'])
 def test_cfg4_three_speakers_8s(D, est):
     """configs[3]: 3 speakers, 8 s (T = 1001), E = 40; anchor estimator (P = 20 subsets) and the k-means plugin

@@ -33,10 +33,11 @@ static inline int pad_k(int K) { return (K + kTK - 1) / kTK * kTK; }
 
 // ---- operand split --------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int Kp, long long lo_row,
+split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int Kp, long long lo_row, int row_perm_T,
                   __nv_bfloat16* __restrict__ out) {
-  // out[0..M) = hi rows, out[lo_row..lo_row+M) = lo rows, each Kp wide
+  // out[0..M) = hi rows, out[lo_row..lo_row+M) = lo rows, each Kp wide; row_perm_T > 0: source row b*T + t -> row t*B + b
   const long long total = (long long)M * (Kp / 2);
+  const int nb = row_perm_T > 0 ? M / row_perm_T : 0;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int m = (int)(i / (Kp / 2)), k = (int)(i % (Kp / 2)) * 2;
     const float x0 = k < K ? __ldg(A + (size_t)m * lda + k) : 0.f;
@@ -44,8 +45,9 @@ split_rows_kernel(const float* __restrict__ A, long long lda, int M, int K, int 
     __nv_bfloat16 h0, l0, h1, l1;
     split_bf16(x0, h0, l0);
     split_bf16(x1, h1, l1);
-    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)m * Kp + k) = __nv_bfloat162(h0, h1);
-    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(lo_row + m) * Kp + k) = __nv_bfloat162(l0, l1);
+    const int mo = row_perm_T > 0 ? (m % row_perm_T) * nb + m / row_perm_T : m;
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)mo * Kp + k) = __nv_bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(lo_row + mo) * Kp + k) = __nv_bfloat162(l0, l1);
   }
 }
 
@@ -725,8 +727,9 @@ struct GemmOperand {
   const float* ptr;
   long long ld;
   int trans;     // 0: stored [rows = own index, cols = K]; 1: stored [rows = K, cols = own index]
-  int perm_T;    // trans == 1 only: K index is time-major over a batch-major source (see split_transpose_kernel)
-  int shift;     // with perm_T: time shift of the source row, zero filled
+  int perm_T;    // trans == 1: K index is time-major over a batch-major source (see split_transpose_kernel);
+                 // trans == 0: source row b*perm_T + t is written to row t*B + b (time-major rows of a batch-major source)
+  int shift;     // with perm_T (trans == 1): time shift of the source row, zero filled
 };
 
 static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloat16* out, long long lo_row,
@@ -736,7 +739,7 @@ static int split_operand(const GemmOperand& op, int R, int K, int Kp, __nv_bfloa
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op.ptr, op.ld, R, K, Kp, lo_row, out);
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op.ptr, op.ld, R, K, Kp, lo_row, op.perm_T, out);
   } else {
     dim3 g(Kp / 32, (R + 31) / 32);
     split_transpose_kernel<<<g, 256, 0, stream>>>(op.ptr, op.ld, K, R, Kp, op.perm_T, op.shift, lo_row, out);
@@ -921,6 +924,18 @@ extern "C" int danet_split_operand(const float* X, long long ld, int stored_k_ma
   return split_operand(op, rows, K, Kp, out, rows_total, as_stream(stream));
 }
 
+// danet_split_operand for a batch-major activation [B*T, K] whose operand rows are wanted TIME-major (row t*B + b): the A
+// operand of danet_gemm_split_pipelined(rows_time_major = 1) for the first recurrent layer
+extern "C" int danet_split_operand_time_major(const float* X, long long ld, int rows, int K, int T, void* out_bf16,
+                                              void* stream) {
+  DANET_REQUIRE(X && out_bf16, DANET_E_ARG, "split_operand_time_major: null pointer");
+  DANET_REQUIRE(rows >= 1 && K >= 1 && T >= 1 && rows % T == 0 && ld >= K, DANET_E_SHAPE,
+                "split_operand_time_major: rows %d K %d T %d ld %lld", rows, K, T, ld);
+  DANET_REQUIRE(aligned16(out_bf16), DANET_E_ALIGN, "split_operand_time_major: out must be 16-byte aligned");
+  GemmOperand op = {X, ld, 0, T, 0};
+  return split_operand(op, rows, K, pad_k(K), reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, as_stream(stream));
+}
+
 extern "C" int danet_split_operand_paired(const float* X, long long ld, int rows, int K, int perm_T, int shift,
                                           void* out_bf16, int row0, int rows_total, void* stream) {
   DANET_REQUIRE(X && out_bf16, DANET_E_ARG, "split_operand_paired: null pointer");
@@ -953,8 +968,12 @@ extern "C" int danet_gemm_split(const void* A2, const void* B2, const float* bia
 // as danet_gemm_split with out_perm_T = T (rows b*T + t of A land at row t*B + b of C), the row tiles issued in the order
 // a forward AND a backward scan over time consume them (tiles holding the first / last frames of an utterance first), and
 // tile_flags[m] counting the finished (column tile, epilogue warp) pairs of row tile m.
+// rows_time_major: A's rows are already t*B + b (danet_lstm_seq_fwd_pipelined's out_split_time_major, or
+// danet_split_operand_time_major): C = A B^T row for row, tiles issued alternately from the two ends of time -- the scans
+// can start once TWO row tiles are done instead of every tile that holds some utterance's first or last frame.
 extern "C" int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M,
-                                          int N, int K, int T, int* tile_flags, int* flag_need, void* stream) {
+                                          int N, int K, int T, int rows_time_major, int* tile_flags, int* flag_need,
+                                          void* stream) {
   DANET_REQUIRE(A2 && B2 && C && tile_flags && flag_need, DANET_E_ARG, "gemm_split_pipelined: null pointer");
   DANET_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N && T >= 1 && M % T == 0, DANET_E_SHAPE,
                 "gemm_split_pipelined: M %d N %d K %d ldc %lld T %d", M, N, K, ldc, T);
@@ -965,10 +984,11 @@ extern "C" int danet_gemm_split_pipelined(const void* A2, const void* B2, const 
   int key[kMaxOrderedTiles];
   unsigned char order[kMaxOrderedTiles];
   for (int m = 0; m < kMaxOrderedTiles; ++m) order[m] = (unsigned char)m;
+  const int nb = M / T;
   for (int m = 0; m < mtiles; ++m) {
     int best = T;
     for (int r = m * kTM; r < (m + 1) * kTM && r < M; ++r) {
-      const int t = r % T, d = t < T - 1 - t ? t : T - 1 - t;
+      const int t = rows_time_major ? r / nb : r % T, d = t < T - 1 - t ? t : T - 1 - t;
       if (d < best) best = d;
     }
     key[m] = best;
@@ -981,5 +1001,5 @@ extern "C" int danet_gemm_split_pipelined(const void* A2, const void* B2, const 
   }
   *flag_need = 4 * ((N + kTN - 1) / kTN);
   return gemm_tc_split(reinterpret_cast<const __nv_bfloat16*>(A2), reinterpret_cast<const __nv_bfloat16*>(B2), bias, C, ldc,
-                       M, N, K, T, 0, as_stream(stream), nullptr, nullptr, 1, tile_flags, order);
+                       M, N, K, rows_time_major ? 0 : T, 0, as_stream(stream), nullptr, nullptr, 1, tile_flags, order);
 }

@@ -61,6 +61,11 @@ struct LstmTcParams {
   // pre_flags[tile] >= flag_need.  A thread waits (acquire) the first time it needs a value of a tile.
   const int* pre_flags;
   int flag_need;
+  // row order of the producer's A operand (and so of its row tiles): 0 = batch-major r = b*T + t, 1 = time-major r = t*B + b
+  int flags_tm;
+  // gen 2: emit out_split with time-major rows (t*B + b) -- the next layer's pipelined product then finishes the tiles
+  // of the first / last frames of ALL utterances first, and its recurrence starts after 2 of its ~32 row tiles
+  int split_tm;
 };
 
 constexpr int kProfSlots = 16;
@@ -556,7 +561,7 @@ lstm_tc2_kernel(const LstmTcParams p) {
       if (valid && s < T) {
         const int to = dir ? T - 1 - s : s;
         if (p.pre_flags) {
-          const int tile = (b * T + to) >> 7;
+          const int tile = (p.flags_tm ? to * B + b : b * T + to) >> 7;
           if (tile != tile_seen) {
             // bounded (~2 s): a producer that never comes must not hang the device -- the values of that tile are then
             // replaced by NaN, which the recurrence carries into every later output of the utterance (a visibly invalid
@@ -684,16 +689,17 @@ lstm_tc2_kernel(const LstmTcParams p) {
         vh = (e & 0xffffu) | (o << 16);
         vl = (e >> 16) | (o & 0xffff0000u);
       }
+      const size_t srow = p.split_tm ? (size_t)to * B + b : (size_t)b * T + to;      // row of the emitted operand
       if (p.zero_pad && odd && b < B && unit >= H) {
         // columns [n_dir*H, out_kp) of the operand: n_dir * (32*ncta - H) of them, one pair per idle unit pair (h = 0 here)
-        __nv_bfloat16* oh = p.out_split + ((size_t)b * T + to) * p.out_kp + p.n_dir * H + dir * (ncta * kUnits - H) + (unit - 1 - H);
+        __nv_bfloat16* oh = p.out_split + srow * p.out_kp + p.n_dir * H + dir * (ncta * kUnits - H) + (unit - 1 - H);
         *reinterpret_cast<uint32_t*>(oh) = 0u;
         *reinterpret_cast<uint32_t*>(oh + (size_t)B * T * p.out_kp) = 0u;
       }
       if (valid) {
         if (odd && p.out_split) {
           if (HF) split2_bf16(he, ho, vh, vl);
-          __nv_bfloat16* oh = p.out_split + ((size_t)b * T + to) * p.out_kp + dir * H + (unit - 1);
+          __nv_bfloat16* oh = p.out_split + srow * p.out_kp + dir * H + (unit - 1);
           *reinterpret_cast<uint32_t*>(oh) = vh;
           *reinterpret_cast<uint32_t*>(oh + (size_t)B * T * p.out_kp) = vl;
         }
@@ -826,7 +832,7 @@ int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H
 int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
                 const void* wh_packed, float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir,
                 int T, int B, int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                const int* pre_flags, int flag_need) {
+                const int* pre_flags, int flag_need, int flags_tm, int split_tm) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
@@ -855,6 +861,7 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   p.zero_pad = 0;
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
   p.pre_flags = pre_flags; p.flag_need = flag_need;
+  p.flags_tm = flags_tm ? 1 : 0; p.split_tm = split_tm ? 1 : 0;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
   const int clusters8 = n_dir * ((B + 7) / 8);
@@ -886,6 +893,8 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   DANET_REQUIRE(!pre_flags || !gen1, DANET_E_SHAPE,
                 "lstm_seq: the pipelined hand-over of the input projections needs the 8-utterances-per-cluster kernel "
                 "(B = %d is too large for co-resident clusters)", B);
+  DANET_REQUIRE(!split_tm || !gen1, DANET_E_SHAPE,
+                "lstm_seq: a time-major out_split is written by the 8-utterances-per-cluster kernel only (B = %d)", B);
   if (gen1) {
     if (out_split && out_kp > n_dir * H)
       DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,

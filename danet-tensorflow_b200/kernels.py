@@ -56,6 +56,7 @@ def _ws(nbytes, device):
 
 
 _timeline = None      # (int64 device tensor, list of labels) while tools/timeline.py records
+_prof_ws = None       # list collecting the pipelined recurrences' workspaces (their in-kernel stamps) for tools/timeline.py
 
 
 def stamp(label):
@@ -320,20 +321,23 @@ def pipeline_flags(device, sets=None):
     return flags
 
 
-def gemm_split_pipelined(a2, b2, m, n, k, T, flags, bias=None):
+def gemm_split_pipelined(a2, b2, m, n, k, T, flags, bias=None, rows_tm=False):
     """gemm_split(out_perm_T=T) that publishes its row tiles through `flags` (int32[64], zeroed by the caller) in the order
-    a forward and a backward scan need them -> (C [m,n], flag_need)  [include/danet.h: danet_gemm_split_pipelined]"""
+    a forward and a backward scan need them -> (C [m,n], flag_need)  [include/danet.h: danet_gemm_split_pipelined].
+    rows_tm: the rows of a2 are already time-major (t*B + b)."""
     out = torch.empty((m, n), dtype=torch.float32, device=a2.device)
     need = C.c_int(0)
-    _lib.check(_lib.load().danet_gemm_split_pipelined(_p(a2), _p(b2), _p(bias), _p(out), n, m, n, k, int(T), _p(flags),
-                                                      C.byref(need), _stream()), 'gemm_split_pipelined')
+    _lib.check(_lib.load().danet_gemm_split_pipelined(_p(a2), _p(b2), _p(bias), _p(out), n, m, n, k, int(T), int(rows_tm),
+                                                      _p(flags), C.byref(need), _stream()), 'gemm_split_pipelined')
     _count()
     return out, need.value
 
 
-def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2, wh_packed=None):
+def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2, wh_packed=None, pre_tm=False,
+                       split_tm=False):
     """lstm_seq(interleaved=True, want_split=True) on input projections that are still being produced by
-    gemm_split_pipelined on another stream -> (hidden [B,T,n_dir*H], its split operand)"""
+    gemm_split_pipelined on another stream -> (hidden [B,T,n_dir*H], its split operand).
+    pre_tm: the producer ran with rows_tm; split_tm: emit the split operand with time-major rows (t*B + b)."""
     pre = _req(pre, 'pre', dim=4)
     n_dir = len(w_list)
     if tuple(pre.shape) != (T, B, n_dir, 4 * H):
@@ -347,9 +351,13 @@ def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2
     out_split = torch.empty((2, B * T, kp), dtype=torch.bfloat16, device=pre.device)
     lib = _lib.load()
     ws = _ws(lib.danet_lstm_seq_workspace_bytes(n_dir, B, H), pre.device)
+    if _prof_ws is not None:             # tools/timeline.py with DANET_LSTM_PROFILE=1: room for the kernel's clock stamps
+        ws = torch.zeros(T * 16 * 8 + 256, dtype=torch.uint8, device=pre.device)
+        _prof_ws.append(ws)
     _lib.check(lib.danet_lstm_seq_fwd_pipelined(_p(pre), 4 * H, n_dir * 4 * H, ptrs, 4 * H, _p(wh_packed), _p(out),
-                                                _p(out_split), kp, n_dir, T, B, H, _p(flags), int(flag_need), _p(ws),
-                                                ws.numel(), int(backend), _stream()), 'lstm_seq_pipelined')
+                                                _p(out_split), kp, n_dir, T, B, H, _p(flags), int(flag_need), int(pre_tm),
+                                                int(split_tm), _p(ws), ws.numel(), int(backend), _stream()),
+               'lstm_seq_pipelined')
     _count()
     return out, out_split
 
@@ -364,6 +372,18 @@ def split_operand(x, k_major_rows, out=None, row0=0, rows_total=None):
         out = torch.empty((2 * rows_total, kp), dtype=torch.bfloat16, device=x.device)
     _lib.check(_lib.load().danet_split_operand(_p(x), x.stride(0), int(k_major_rows), rows, Kd, _p(out), row0, rows_total,
                                                _stream()), 'split_operand')
+    _count()
+    return out
+
+
+def split_operand_time_major(x, T):
+    """batch-major fp32 [B*T, K] -> bf16 [2*B*T, Kp] hi/lo operand with TIME-major rows (t*B + b)"""
+    x = _req_strided(x, 'x')
+    rows, Kd = x.shape
+    kp = (Kd + 63) // 64 * 64
+    out = torch.empty((2 * rows, kp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().danet_split_operand_time_major(_p(x), x.stride(0), rows, Kd, int(T), _p(out), _stream()),
+               'split_operand_time_major')
     _count()
     return out
 

@@ -36,7 +36,7 @@ class Model(object):
         self._graphs = {}
         self._packed = {}                 # weights pre-split for the tensor cores (dropped whenever they change)
         self._packed_ready = False        # True once every entry exists (built on ONE stream, see _prepare_packed)
-        self._last_split = None           # (hidden sequence, its split copy) handed from layer to layer
+        self._last_split = None           # (hidden sequence, its split copy, rows time-major?) handed from layer to layer
         self._tape = None                 # training: saved activations per recurrent layer
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
         self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
@@ -138,11 +138,15 @@ class Model(object):
         pre = K.linear(x2, W, Bv, time_major_T=T, k_rows=I).view(1, T, B, 4 * hdim)
         if reverse:
             raise NotImplementedError('single reversed direction: use lyr_bilstm')
+        wide = K.DEFAULT_BACKEND == 1 and K.TC_LSTM_MAX_H < hdim <= K.TC_WIDE_MAX_H
         if self._tape is not None:
-            out, cell = K.lstm_seq(pre, [W], I, T, B, hdim, keep_cell=True, keep_gates=True)
+            # training forward of a wide layer (lstm-orig): the wide tcgen05 kernel keeps cell states and gates as the
+            # exact-fp32 kernel does (the weights change every step, so the image is packed by the library on the fly)
+            out, cell = K.lstm_seq(pre, [W], I, T, B, hdim, keep_cell=True, keep_gates=True,
+                                   backend=2 if wide and self.train_recurrent_fp16() else None)
             self._tape.append(dict(name=name, x=s_x, gates=pre, cell=cell, out=out, hdim=hdim))
             return out
-        if (self.RECURRENT_FP16 and K.DEFAULT_BACKEND == 1 and K.TC_LSTM_MAX_H < hdim <= K.TC_WIDE_MAX_H):
+        if self.RECURRENT_FP16 and wide:
             # lstm-orig (H = 600) in inference: the wide tcgen05 kernel on a cached weight image (fp16 state, C-ABI backend 2)
             wh_packed = self._packed.get(name + '/wh')
             if wh_packed is None:
@@ -183,11 +187,20 @@ class Model(object):
         return 2 if self.RECURRENT_FP16 else 1
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
     PIPELINE_INPUT_GEMM = True # the recurrence starts on the first finished tiles of its input projections
+    TIME_MAJOR_HANDOVER = True # ... whose A operand has time-major rows, so that 2 finished row tiles are enough to start
+    _emit_time_major = False   # set by the encoder around a layer whose output feeds another pipelined recurrent layer
     # training forward: carry h into the recurrent product as fp16 as inference does (0.57 -> 0.47 ms per layer at cfg 2,
-    # step 9.38 -> 9.14 ms).  OFF: against float64 autograd on the oracle the bilstm-orig gradients move only from 2.9e-5 to
-    # 4.2e-5 (tools/train_precision.py), but the reference-generated gradient fixture of conv-bilstm-v1 fails its 1e-3 gate
-    # with it (first convolution's kernel: 3.3e-3 -- the max-pools turn the 1e-4 forward deviation into routing changes).
-    TRAIN_RECURRENT_FP16 = False
+    # step 9.38 -> 9.14 ms).  None = the encoder decides (its TRAIN_FP16_STATE_OK): on for the purely recurrent encoders --
+    # against float64 autograd on the oracle the bilstm-orig gradients move only from 2.9e-5 to 4.2e-5 of their variable's
+    # largest entry (tools/train_precision.py) -- and off for conv-bilstm-v1, whose reference-generated gradient fixture
+    # fails its 1e-3 gate with it (first convolution's kernel: 3.3e-3 -- the max-pools turn the 1e-4 forward deviation into
+    # routing changes).  True / False force it for A/B runs.
+    TRAIN_RECURRENT_FP16 = None
+
+    def train_recurrent_fp16(self):
+        if self.TRAIN_RECURRENT_FP16 is not None:
+            return bool(self.TRAIN_RECURRENT_FP16)
+        return bool(getattr(self.encoder, 'TRAIN_FP16_STATE_OK', False))
 
     FLAG_SETS = 8              # completion-flag sets cleared by ONE launch per group and step (one set per recurrent layer)
 
@@ -216,10 +229,18 @@ class Model(object):
             self._packed[name] = ent
         w2, bias2, wh_packed = ent
         prev = self._last_split
-        a2 = prev[1] if prev is not None and prev[0] is s_x else K.split_operand(s_x.reshape(B * T, I), False)
         backend = self.recurrent_backend()
-        if (self.PIPELINE_INPUT_GEMM and self.LSTM_PRIORITY_STREAM and B * T <= K.PIPELINE_MAX_ROWS
-                and B <= self.PIPELINE_GROUP and wh_packed is not None):
+        pipelined = (self.PIPELINE_INPUT_GEMM and self.LSTM_PRIORITY_STREAM and B * T <= K.PIPELINE_MAX_ROWS
+                     and B <= self.PIPELINE_GROUP and wh_packed is not None)
+        # rows of the product's A operand in TIME-major order (t*B + b): the first / last row tile then serve the first /
+        # last 16 steps of every utterance and the scans start after 2 tiles of the product instead of ~9 of its 32
+        if prev is not None and prev[0] is s_x:
+            a2, a_tm = prev[1], prev[2]
+        elif pipelined and self.TIME_MAJOR_HANDOVER:
+            a2, a_tm = K.split_operand_time_major(s_x.reshape(B * T, I), T), True
+        else:
+            a2, a_tm = K.split_operand(s_x.reshape(B * T, I), False), False
+        if pipelined:
             # The recurrence does not wait for the whole product: the GEMM issues its row tiles in the order the two scans
             # consume them and publishes each through a flag; the recurrent kernel, launched from its high-priority stream
             # as soon as the product has been QUEUED, spins on the flag of the tile it is about to read
@@ -233,7 +254,7 @@ class Model(object):
                 # give the recurrence's 10-CTA clusters first pick of the SMs: launched at the same moment, the product's
                 # single CTAs fill SMs one by one and a cluster never finds ten free ones in a GPC until the product drains
                 torch.cuda._sleep(int(self.LSTM_HEADSTART_US * 1840))
-            pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * hdim, I, T, flags, bias=bias2)
+            pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * hdim, I, T, flags, bias=bias2, rows_tm=a_tm)
             pre = pre.view(T, B, 2, 4 * hdim)
             if self._stagger_pending:
                 self._stagger_pending = False
@@ -242,13 +263,16 @@ class Model(object):
             K.stamp('%s gemm' % name)
             hp_stream.wait_event(queued)
             with torch.cuda.stream(hp_stream):
+                # only a layer that feeds another recurrent layer may emit time-major rows (the output projection cuts
+                # its row tiles per utterance): the encoder says so through _emit_time_major
+                emit_tm = bool(self.TIME_MAJOR_HANDOVER and self._emit_time_major)
                 out, out_split = K.lstm_seq_pipelined(pre, [Wf, Wb], I, T, B, hdim, flags, need, backend=backend,
-                                                      wh_packed=wh_packed)
+                                                      wh_packed=wh_packed, pre_tm=a_tm, split_tm=emit_tm)
             cur.wait_stream(hp_stream)
             K.stamp('%s lstm' % name)
-            self._last_split = (out, out_split)
+            self._last_split = (out, out_split, emit_tm)
             return out
-        pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=T).view(T, B, 2, 4 * hdim)
+        pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=0 if a_tm else T).view(T, B, 2, 4 * hdim)
         if self._stagger_pending:          # see separate(): the next stream group may start now
             self._stagger_pending = False
             self._stagger_event = torch.cuda.current_stream().record_event()
@@ -267,7 +291,7 @@ class Model(object):
             out, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, interleaved=True, want_split=True,
                                         wh_packed=wh_packed, backend=backend)
         K.stamp('%s lstm' % name)
-        self._last_split = (out, out_split)
+        self._last_split = (out, out_split, False)
         return out
 
     def centered_projection(self, name, x, W):
@@ -275,7 +299,8 @@ class Model(object):
         recurrent layer already emitted: (x - mu) W = x W - mu colsum(W), the rank-1 term applied in the epilogue.
         Returns None when the fast path does not apply."""
         prev = self._last_split
-        if not self.USE_CENTER_FOLD or self._tape is not None or K.DEFAULT_BACKEND != 1 or prev is None or prev[0] is not x:
+        if (not self.USE_CENTER_FOLD or self._tape is not None or K.DEFAULT_BACKEND != 1 or prev is None or prev[0] is not x
+                or prev[2]):                   # prev[2]: the operand's rows are time-major (never for the last layer)
             return None
         ent = self._packed.get(name)
         if ent is None:
@@ -343,8 +368,8 @@ class Model(object):
                 K.gemm_split(a2, K.split_operand(W[:I], True), B * T, 4 * hdim, I, bias=Bv, out_perm_T=T,
                              out=pre[d].view(T * B, 4 * hdim))
             out, cell, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True, want_split=True,
-                                              backend=2 if self.TRAIN_RECURRENT_FP16 else None)
-            self._last_split = (out, out_split)
+                                              backend=2 if self.train_recurrent_fp16() else None)
+            self._last_split = (out, out_split, False)
         else:
             K.linear(x2, Wf, Bf, time_major_T=T, k_rows=I, out=pre[0].view(T * B, 4 * hdim))
             K.linear(x2, Wb, Bb, time_major_T=T, k_rows=I, out=pre[1].view(T * B, 4 * hdim))

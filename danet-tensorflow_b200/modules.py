@@ -159,6 +159,7 @@ class _RecurrentEncoder(Encoder):
     HDIM = 300
     INIT_SCALE = .75
     BIDIR = True
+    TRAIN_FP16_STATE_OK = True     # Model.TRAIN_RECURRENT_FP16: the training forward may carry h as fp16 (measured, model.py)
 
     def _geometry(self):
         n_layers = getattr(hparams, 'ENCODER_LAYERS', None) or self.N_LAYERS
@@ -176,7 +177,12 @@ class _RecurrentEncoder(Encoder):
         b_init = lambda rs, shape: lstm_bias_init(hdim)
         for l in range(n_layers):
             if self.BIDIR:
-                x = _lyr_bilstm('%s/lstm%d' % (self.name, l), model, x, hdim, w_init, b_init, s_dropout_keep)
+                # a layer that feeds another recurrent layer may hand its output over with time-major rows (model.py)
+                model._emit_time_major = l + 1 < n_layers
+                try:
+                    x = _lyr_bilstm('%s/lstm%d' % (self.name, l), model, x, hdim, w_init, b_init, s_dropout_keep)
+                finally:
+                    model._emit_time_major = False
             else:
                 x = model.lyr_lstm('%s/lstm%d' % (self.name, l), x, hdim, w_init=w_init, b_init=b_init)
         odim = x.shape[-1]

@@ -131,6 +131,10 @@ int danet_split_operand(const float* X, long long ld, int stored_k_major_rows, i
                         void* out_bf16, int row0, int rows_total, void* stream);
 int danet_split_operand_paired(const float* X, long long ld, int rows, int K, int perm_T, int shift,
                                void* out_bf16, int row0, int rows_total, void* stream);
+/*   danet_split_operand_time_major: danet_split_operand for a batch-major activation X [B*T, K] (main.py:76-132 feeds the
+ *     scan time-major: `tf.transpose(s_x, [1, 0, 2])`) whose operand rows are wanted time-major: source row b*T + t is
+ *     written to row t*B + b of out [2*rows, Kp] -- the A operand of danet_gemm_split_pipelined(rows_time_major = 1). */
+int danet_split_operand_time_major(const float* X, long long ld, int rows, int K, int T, void* out_bf16, void* stream);
 int danet_gemm_split(const void* A2, const void* B2, const float* bias, const float* row_mu,
                      const float* col_s, int rows_per_mu, float* C, long long ldc,
                      int M, int N, int K, int out_perm_T, int accumulate, void* stream);
@@ -149,13 +153,19 @@ int danet_gemm_split(const void* A2, const void* B2, const float* bias, const fl
 /* zero `bytes` (multiple of 4) at ptr on `stream`; small buffers by a one-block kernel (cheaper than a memset node inside a
  * captured graph): clears tile_flags */
 int danet_zero_async(void* ptr, size_t bytes, void* stream);
+/*   rows_time_major / pre_rows_time_major: A's rows are t*B + b instead of b*T + t (danet_split_operand_time_major, or the
+ *     previous layer's recurrence called with out_split_time_major): the first and the last 128-row tile then hold the
+ *     first / last 16 frames of ALL 8 utterances, the product issues its tiles alternately from the two ends of time, and
+ *     both scans start after 2 of the ~32 row tiles instead of after every tile that holds some utterance's first or last
+ *     frame (~9).  out_split_time_major: the recurrence emits its out_split in that row order. */
 int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M, int N,
-                               int K, int T, int* tile_flags, int* flag_need, void* stream);
+                               int K, int T, int rows_time_major, int* tile_flags, int* flag_need, void* stream);
 int danet_lstm_seq_fwd_pipelined(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                                  const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
                                  void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
-                                 const int* pre_flags, int flag_need, void* workspace, size_t workspace_bytes,
-                                 int backend, void* stream);
+                                 const int* pre_flags, int flag_need, int pre_rows_time_major,
+                                 int out_split_time_major, void* workspace, size_t workspace_bytes, int backend,
+                                 void* stream);
 
 /* ---- K2c + K3 fused: output projection with the anchor estimator's sums in its epilogue ----
  * replaces, in ONE kernel + a per-utterance finalize, the mean-centred bias-free output layer of the encoder

@@ -885,10 +885,13 @@ def test_fused_inference_path_equals_unfused(D):
     assert float((fused - plain).abs().max() / plain.abs().max()) < 2e-4
 
 
+@pytest.mark.parametrize('tm', [False, True], ids=['batch-major-rows', 'time-major-rows'])
 @pytest.mark.parametrize('B,T,I,backend', [(8, 501, 600, 2), (8, 501, 129, 1), (3, 40, 600, 2), (8, 1001, 600, 2)])
-def test_pipelined_input_projection_handover(K, B, T, I, backend):
+def test_pipelined_input_projection_handover(K, B, T, I, backend, tm):
     """danet_gemm_split_pipelined + danet_lstm_seq_fwd_pipelined: the recurrence launched on a second stream BEFORE its input
-    projections exist, synchronised tile by tile through the flags, gives bit-identical results to product-then-recurrence"""
+    projections exist, synchronised tile by tile through the flags, gives bit-identical results to product-then-recurrence.
+    tm: the product's A operand has time-major rows (danet_split_operand_time_major) and the recurrence emits its split
+    operand time-major as well -- the same numbers, permuted"""
     H = 300
     rs = np.random.RandomState(T + I)
     r = .75 / np.sqrt(H)
@@ -911,13 +914,22 @@ def test_pipelined_input_projection_handover(K, B, T, I, backend):
         queued = cur.record_event()
         if rep:
             torch.cuda._sleep(2000000)
-        pre, need = K.gemm_split_pipelined(a2, w2, B * T, 8 * H, I, T, flags, bias=bias)
+        a2_used = K.split_operand_time_major(x, T) if tm else a2
+        if tm:
+            kp = a2.shape[-1]
+            assert torch.equal(a2_used.view(2, T, B, kp), a2.view(2, B, T, kp).transpose(1, 2))
+        pre, need = K.gemm_split_pipelined(a2_used, w2, B * T, 8 * H, I, T, flags, bias=bias, rows_tm=tm)
         side.wait_event(queued)
         with torch.cuda.stream(side):
             out, split = K.lstm_seq_pipelined(pre.view(T, B, 2, 4 * H), Ws, I, T, B, H, flags, need, backend=backend,
-                                              wh_packed=packed)
+                                              wh_packed=packed, pre_tm=tm, split_tm=tm)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         assert torch.equal(pre.view(T, B, 2, 4 * H), pre_ref)
         assert int(flags[:(B * T + 127) // 128].min()) == need and int(flags[(B * T + 127) // 128:].max()) == 0
-        assert torch.equal(out, out_ref) and torch.equal(split, split_ref)
+        assert torch.equal(out, out_ref)
+        if tm:
+            kp = split_ref.shape[-1]
+            assert torch.equal(split.view(2, T, B, kp), split_ref.view(2, B, T, kp).transpose(1, 2))
+        else:
+            assert torch.equal(split, split_ref)

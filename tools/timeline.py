@@ -9,6 +9,10 @@ K = D.kernels
 hp = D.hparams
 hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
              SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=32)); hp.digest()
+for kv in os.environ.get('DANET_AB', '').split(','):          # e.g. DANET_AB=LSTM_HEADSTART_US=4,TIME_MAJOR_HANDOVER=0
+    if kv:
+        k, v = kv.split('=')
+        setattr(D.Model, k, type(getattr(D.Model, k))(int(v)))
 model = D.Model('t', 'cuda:0').build()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32000          # samples per utterance (T = N/64 + 1 frames)
 HOST = len(sys.argv) > 2 and sys.argv[2] == 'host'             # pinned host buffers in and out (the e2e call)
@@ -20,12 +24,16 @@ for _ in range(2):
 buf = torch.zeros(4096, dtype=torch.int64, device='cuda')
 labels = []
 K._timeline = (buf, labels)
+PROF = bool(os.environ.get('DANET_LSTM_PROFILE'))
+if PROF:
+    K._prof_ws = []
 graph = torch.cuda.CUDAGraph()
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
     with torch.cuda.graph(graph, stream=side):
         y = model.separate(wav, out=out_host)
 K._timeline = None
+prof_ws, K._prof_ws = K._prof_ws, None
 for _ in range(3):
     graph.replay()
 torch.cuda.synchronize()
@@ -47,3 +55,16 @@ for g in order:
         print('  %-28s at %8.1f us  (+%7.1f)' % (lab, ts, ts - prev if prev is not None else 0.))
         prev = ts
 print('N = %d samples, %s: total %.1f us' % (N, 'pinned host in/out' if HOST else 'device resident', (t.max() - t0) / 1e3))
+
+if PROF:
+    # in-kernel stamps of CTA (0,0,0) of every pipelined recurrence (launch order = group-major, 4 layers each):
+    # %globaltimer at kernel entry / exit, SM clock at entry / prologue end / step s
+    print('recurrent kernels, CTA (0,0,0): entry and exit by %globaltimer (us on the timeline above), clock stamps')
+    for i, ws in enumerate(prof_ws):
+        p = ws[:501 * 16 * 8].view(torch.int64).view(-1, 16).cpu().numpy()
+        ent, ext = (p[0, 14] - t0) / 1e3, (p[0, 15] - t0) / 1e3
+        ck = lambda a: a / 1840.
+        e = p[0, 10]
+        print('  #%02d entry %8.1f exit %8.1f | prologue %5.1f us, step 1 done +%5.1f, step 16 +%5.1f, step 32 +%5.1f, step 64 +%5.1f, step 250 +%6.1f, loop end +%6.1f'
+              % (i, ent, ext, ck(p[0, 11] - e), ck(p[1, 7] - e), ck(p[16, 7] - e), ck(p[32, 7] - e), ck(p[64, 7] - e),
+                 ck(p[250, 7] - e), ck(p[0, 12] - e)))

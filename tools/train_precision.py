@@ -50,4 +50,4 @@ for fp16 in (0, 1, 0, 1):
         ts.append(e0.elapsed_time(e1))
     print('forward state fp16 = %d: train step %.3f ms (%.0f mixtures/s)' % (fp16, np.median(ts), 32 / np.median(ts) * 1e3))
     del m
-D.Model.TRAIN_RECURRENT_FP16 = False
+D.Model.TRAIN_RECURRENT_FP16 = None

@@ -56,6 +56,7 @@ struct LstmTcParams {
   long long pre_dir, pre_row;   // element strides of pre: address = dir*pre_dir + (t*B + b)*pre_row + gate*H + unit
   int n_dir, T, B, H;
   long long* prof;         // nullable: per-step phase timestamps of CTA (0,0,0) (DANET_LSTM_PROFILE=1)
+  int prof_steps;          // 0: entry / exit stamps only (DANET_LSTM_PROFILE=2)
   // nullable: the input projections are still being PRODUCED while this kernel runs (danet_gemm_split_pipelined on another
   // stream): row r = b*T + t of the producer's A operand belongs to row tile r / 128, complete once
   // pre_flags[tile] >= flag_need.  A thread waits (acquire) the first time it needs a value of a tile.
@@ -427,9 +428,12 @@ lstm_tc2_kernel(const LstmTcParams p) {
 
   const int unit0 = rank * kUnits;
   const int b0 = bt * NB;
-  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
+  // DANET_LSTM_PROFILE=2: only the entry / exit stamps of row 0 (no per-step stamps, no memset ahead of the launch: the
+  // timing of the step is not disturbed)
+  const bool prof_ee = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  const bool prof_on = p.prof != nullptr && p.prof_steps && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
                        (tid == 0 || warp == kMmaWarp || warp == kSend0);
-  if (prof_on && tid == 0) {
+  if (prof_ee) {
     p.prof[10] = clock64();
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -509,7 +513,7 @@ lstm_tc2_kernel(const LstmTcParams p) {
   __syncthreads();
   tc_fence_after();
   cluster_sync();
-  if (prof_on && tid == 0) p.prof[11] = clock64();
+  if (prof_ee) p.prof[11] = clock64();
 
   if (warp == kMmaWarp) {
     // ================= MMA issuer =================
@@ -732,12 +736,12 @@ lstm_tc2_kernel(const LstmTcParams p) {
       __syncwarp();
     }
   }
-  if (prof_on && tid == 0) p.prof[12] = clock64();
+  if (prof_ee) p.prof[12] = clock64();
   tc_fence_before();
   __syncthreads();
   cluster_sync();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
-  if (prof_on && tid == 0) {
+  if (prof_ee) {
     p.prof[13] = clock64();
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -841,9 +845,11 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
                 "lstm_seq: pre/out/cell_seq must be 16-byte aligned");
   DANET_REQUIRE(!wh_packed || aligned16(wh_packed), DANET_E_ALIGN, "lstm_seq: wh_packed must be 16-byte aligned");
   long long* prof = nullptr;
+  int prof_steps = 1;
   if (getenv("DANET_LSTM_PROFILE") && workspace && workspace_bytes >= (size_t)T * kProfSlots * sizeof(long long)) {
     prof = reinterpret_cast<long long*>(workspace);
-    DANET_CUDA(cudaMemsetAsync(prof, 0, (size_t)T * kProfSlots * sizeof(long long), stream));
+    prof_steps = atoi(getenv("DANET_LSTM_PROFILE")) != 2;
+    if (prof_steps) DANET_CUDA(cudaMemsetAsync(prof, 0, (size_t)T * kProfSlots * sizeof(long long), stream));
   }
   LstmTcParams p;
   p.pre = pre;
@@ -859,7 +865,7 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
                   "lstm_seq: out_split needs a 16-byte aligned buffer with row length %d >= %d, multiple of 64", out_kp, n_dir * H);
   }
   p.zero_pad = 0;
-  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof;
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof; p.prof_steps = prof_steps;
   p.pre_flags = pre_flags; p.flag_need = flag_need;
   p.flags_tm = flags_tm ? 1 : 0; p.split_tm = split_tm ? 1 : 0;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and

@@ -65,6 +65,10 @@ if PROF:
         ent, ext = (p[0, 14] - t0) / 1e3, (p[0, 15] - t0) / 1e3
         ck = lambda a: a / 1840.
         e = p[0, 10]
+        if os.environ['DANET_LSTM_PROFILE'] == '2':       # entry / exit only: the undisturbed schedule
+            print('  #%02d (group %d, layer %d) entry %8.1f  exit %8.1f  = %6.1f us in the kernel, prologue %4.1f us'
+                  % (i, i // 4, i % 4, ent, ext, ext - ent, ck(p[0, 11] - e)))
+            continue
         print('  #%02d entry %8.1f exit %8.1f | prologue %5.1f us, step 1 done +%5.1f, step 16 +%5.1f, step 32 +%5.1f, step 64 +%5.1f, step 250 +%6.1f, loop end +%6.1f'
               % (i, ent, ext, ck(p[0, 11] - e), ck(p[1, 7] - e), ck(p[16, 7] - e), ck(p[32, 7] - e), ck(p[64, 7] - e),
                  ck(p[250, 7] - e), ck(p[0, 12] - e)))

@@ -405,29 +405,45 @@ def main():
     train = None
     if args.train_steps > 0:
         src = K.stft(torch.from_numpy(synth_sources(B, N_SAMPLES, 1337 + rank)).to(dev))     # [B,C,T,F] complex
-        for _ in range(3):
+        for _ in range(4):                       # two eager steps, the capture of forward + backward, one replay
             model.train_step(src)
         model.TIME_ALLREDUCE = True
         model._ar_events = []
-        K.launches = 0
-        kernel_events.clear()
-        Timed.on = True
         ms_train = timed_loop(lambda: model.train_step(src), args.train_steps)
-        Timed.on = False
         model.TIME_ALLREDUCE = False
         ar_ms = [a.elapsed_time(b) for a, b in model._ar_events]
         ar_exposed = D.shard.max_over_ranks(float(np.mean(ar_ms)) if ar_ms else 0., dev)
+        # the timed steps replay forward + backward from a CUDA graph (two stream groups): events cannot be read back from
+        # inside a replay and our launch counter does not run, so (a) the launches of the TIMED schedule are counted on one
+        # eager step of the same grouped schedule, (b) the BPTT / forward recurrence kernels are timed on eager one-pass steps
+        groups_timed = model._train_group_count(B)
+        model.TRAIN_GRAPH = False
+        K.launches = 0
+        model.train_step(src)
+        torch.cuda.synchronize()
+        train_launches = K.launches
+        model.TRAIN_GROUPS = 1
+        kernel_events.clear()
+        Timed.on = True
+        for _ in range(3):
+            model.train_step(src)
+        torch.cuda.synchronize()
+        Timed.on = False
+        del model.TRAIN_GROUPS, model.TRAIN_GRAPH          # back to the class defaults
         bptt = [a.elapsed_time(b) for a, b in kernel_events.get('lstm_seq_bwd', [])]
         fwd_l = [a.elapsed_time(b) for a, b in kernel_events.get('lstm_seq', [])]
         n_param = int(model._flat['grad'].numel())
         train = {'value': B * world * args.train_steps / (ms_train / 1e3), 'unit': 'mixtures/s',
                  'ms_per_step': ms_train / args.train_steps, 'steps': args.train_steps, 'n_gpus': world,
-                 'global_batch': B * world, 'gpu_launches': K.launches // args.train_steps,
+                 'global_batch': B * world, 'gpu_launches': train_launches, 'stream_groups': groups_timed,
                  'allreduce_ms_exposed': ar_exposed, 'allreduce_bytes': 4 * n_param,
-                 'allreduce': 'NCCL, 5 buckets in backward completion order (projection + anchors, L3 .. L0), each started '
-                              'on the stream that produced it; exposed = what the step still waits for after the backward',
+                 'allreduce': ('NCCL, one exchange of the flat gradient buffer after the stream groups\' gradients are summed; '
+                               'exposed = its whole duration' if groups_timed > 1 else
+                               'NCCL, 5 buckets in backward completion order (projection + anchors, L3 .. L0), each started '
+                               'on the stream that produced it; exposed = what the step still waits for after the backward'),
                  'what': 'spectra resident in HBM -> forward, PIT-MSE, backward (tcgen05 cluster BPTT + tcgen05 dW/dX '
-                         'products), bucketed gradient all-reduce (N > 1), fused clip + Adam'}
+                         'products) in %d stream groups replayed from a CUDA graph, gradient all-reduce (N > 1), fused '
+                         'clip + Adam' % groups_timed}
         if bptt:
             bflops = 2. * 2 * B * HDIM * 4 * HDIM * T           # dh = da * Wh^T, both directions, per launch
             bms = float(np.mean(bptt))

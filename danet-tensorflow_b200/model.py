@@ -37,6 +37,9 @@ class Model(object):
         self._packed = {}                 # weights pre-split for the tensor cores (dropped whenever they change)
         self._packed_ready = False        # True once every entry exists (built on ONE stream, see _prepare_packed)
         self._last_split = None           # (hidden sequence, its split copy, rows time-major?) handed from layer to layer
+        self._group_grad_bufs = {}        # training slice g >= 1 -> (flat gradient buffer, per-variable views)
+        self._train_graphs, self._train_warm = {}, {}     # captured forward + backward per input shape
+        self._in_train_group, self._train_group = False, 0
         self._tape = None                 # training: saved activations per recurrent layer
         self._flat = None                 # training: (param, grad, adam m, adam v) flat buffers + views
         self._buckets = None              # training: per-layer all-reduce of slices of the flat gradient buffer
@@ -367,6 +370,9 @@ class Model(object):
             for d, (W, Bv) in enumerate(((Wf, Bf), (Wb, Bb))):
                 K.gemm_split(a2, K.split_operand(W[:I], True), B * T, 4 * hdim, I, bias=Bv, out_perm_T=T,
                              out=pre[d].view(T * B, 4 * hdim))
+            if self._stagger_pending:      # train_forward_backward in stream groups: the next slice may start now
+                self._stagger_pending = False
+                self._stagger_event = torch.cuda.current_stream().record_event()
             out, cell, out_split = K.lstm_seq(pre, [Wf, Wb], I, T, B, hdim, keep_cell=True, keep_gates=True, want_split=True,
                                               backend=2 if self.train_recurrent_fp16() else None)
             self._last_split = (out, out_split, False)
@@ -394,6 +400,7 @@ class Model(object):
         self._flat = dict(param=flat, grad=grad, m=torch.zeros_like(flat), v=torch.zeros_like(flat), offs=offs)
         self.grads = {k: grad[offs[k]:offs[k] + self.params[k].numel()].view(self.params[k].shape) for k in names}
         self._buckets = shard.GradientBuckets(grad, {k: (offs[k], offs[k] + self.params[k].numel()) for k in names})
+        self._train_graphs, self._train_warm, self._group_grad_bufs = {}, {}, {}     # they point into the old buffers
         return self._flat
 
     BUCKETED_ALLREDUCE = True          # N > 1: all-reduce each layer's gradients as soon as they are queued (under BPTT)
@@ -402,8 +409,34 @@ class Model(object):
     def grads_ready(self, names):
         """called by an encoder's backward on the stream that produced the gradients of `names`: their slice of the flat
         buffer may be exchanged now (no-op on one rank)"""
-        if self.BUCKETED_ALLREDUCE and self._flat is not None:
+        if self.BUCKETED_ALLREDUCE and self._flat is not None and not self._in_train_group:
             self._buckets.reduce(names)
+
+    # Training step in stream groups (the inference schedule applied to training): the batch is cut into TRAIN_GROUPS
+    # slices that run forward + backward on their own streams, one dense layer apart, so that one slice's products fill
+    # the SMs the other slices' latency-bound recurrences (20 SMs per 8 utterances and direction) leave idle.  Every slice
+    # writes its own flat gradient buffer; the step's gradient is their batch-weighted sum (the loss is a batch mean,
+    # app/ops.py:406-431), exact up to summation order.  On N > 1 ranks the exchange then runs once after the sum instead of
+    # in per-layer buckets under the backward pass.  0 / 1 = the whole batch in one pass.  Measured at cfg 2 (B = 32, graph
+    # replay, tools/time_train_groups.py): 9.34 ms in one pass, 8.88 ms in two slices, 10.0 ms in four -- unlike inference
+    # the step is not latency-bound once sliced: a slice of 8 alone takes 6.35 ms (16: 7.25 ms), but the dense / streaming
+    # work of a step (3.4 ms of the whole machine) has only the 68 SMs the recurrences leave.
+    TRAIN_GROUPS = 2
+    TRAIN_GROUP_MIN = 8                # utterances per slice at least (one recurrent cluster's batch tile)
+
+    def _train_group_count(self, B):
+        n = int(self.TRAIN_GROUPS or 1)
+        return max(1, min(n, B // max(1, int(self.TRAIN_GROUP_MIN))))
+
+    def _group_grads(self, g):
+        """flat gradient buffer + per-variable views of training slice g >= 1 (slice 0 writes the model's own)"""
+        ent = self._group_grad_bufs.get(g)
+        if ent is None or ent[0].numel() != self._flat['grad'].numel():
+            buf = torch.zeros_like(self._flat['grad'])
+            offs = self._flat['offs']
+            views = {k: buf[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in self.params.items()}
+            ent = self._group_grad_bufs[g] = (buf, views)
+        return ent
 
     def train_forward_backward(self, src):
         """One forward + backward of the train loss (main.py:289, 357-358) on complex spectra src [B,C,T,F];
@@ -417,6 +450,44 @@ class Model(object):
         if est_name not in ('anchor', 'truth', 'truth-threshold', 'truth-weighted'):
             raise NotImplementedError('no backward for estimator %r' % est_name)
         src = src.to(self.device)
+        B = src.shape[0]
+        groups = self._train_group_count(B)
+        if groups <= 1:
+            return self._train_forward_backward_slice(src)
+        self._ensure_variables()           # created on ONE stream, in the reference's order, before the slices fork
+        main = torch.cuda.current_stream()
+        fork = main.record_event()
+        streams = self._side_streams(groups)
+        own_grads, outs, sizes, prev = self.grads, [], [], None
+        self._in_train_group = True        # grads_ready(): no per-layer exchange of a slice's partial gradient
+        try:
+            for g, st in enumerate(streams):
+                lo, hi = shard.shard_bounds(B, g, groups)
+                st.wait_event(fork)
+                if prev is not None:
+                    st.wait_event(prev)    # stagger: slice g starts when slice g-1 has queued its first dense layer
+                with torch.cuda.stream(st):
+                    self.grads = own_grads if g == 0 else self._group_grads(g)[1]
+                    self._train_group = g
+                    self._stagger_pending, self._stagger_event = True, None
+                    outs.append(self._train_forward_backward_slice(src[lo:hi]))
+                    prev = self._stagger_event
+                    self._stagger_pending = False
+                sizes.append(hi - lo)
+        finally:
+            self.grads, self._train_group, self._in_train_group = own_grads, 0, False
+        for st in streams:
+            main.wait_stream(st)
+        flat = self._flat['grad']
+        flat.mul_(sizes[0] / B)
+        for g in range(1, groups):
+            flat.add_(self._group_grads(g)[0], alpha=sizes[g] / B)
+        w = [n / B for n in sizes]
+        return dict(loss=sum(o['loss'] * wi for o, wi in zip(outs, w)), snr=sum(o['snr'] * wi for o, wi in zip(outs, w)),
+                    perm_idx=torch.cat([o['perm_idx'] for o in outs]))
+
+    def _train_forward_backward_slice(self, src):
+        est_name = hparams.TRAIN_ESTIMATOR_METHOD
         B, Cn, T, F = src.shape
         E = hparams.EMBED_SIZE
         feats = K.mix_features(src)
@@ -471,9 +542,36 @@ class Model(object):
         else:
             K.clip_sgd(f['param'], f['grad'], opt['lr'], clip=hparams.GRAD_CLIP_THRES, grad_scale=grad_scale)
 
+    # The forward + backward of a training step replayed from a CUDA graph captured once per input shape (after two eager
+    # steps): with the batch in stream groups a step is ~1500 launches, and queued from Python they take longer than the
+    # GPU needs (measured: 4 groups eager 14.4 ms per step against 9.5 ms for one pass).  The variables live in the flat
+    # buffer and are updated in place, so the captured pointers stay valid; the exchange and the optimiser run outside.
+    TRAIN_GRAPH = True
+
+    def train_forward_backward_graphed(self, src):
+        key = (tuple(src.shape), self._train_group_count(src.shape[0]), hparams.TRAIN_ESTIMATOR_METHOD,
+               hparams.SEPARATOR_TYPE)
+        ent = self._train_graphs.get(key)
+        if ent is None:
+            n = self._train_warm.get(key, 0)
+            if n < 2 or self._flat is None:        # variables, flat buffers, allocator, kernel attributes: eagerly first
+                self._train_warm[key] = n + 1
+                return self.train_forward_backward(src)
+            static_src = src.to(self.device).clone()
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.train_forward_backward(static_src)
+            ent = self._train_graphs[key] = (graph, static_src, out)
+        graph, static_src, out = ent
+        if src.data_ptr() != static_src.data_ptr():
+            static_src.copy_(src, non_blocking=True)
+        graph.replay()
+        return out
+
     def train_step(self, src):
         """train fetches (main.py:369-375): forward, backward, gradient all-reduce, clip + optimiser"""
-        out = self.train_forward_backward(src)
+        out = self.train_forward_backward_graphed(src) if self.TRAIN_GRAPH else self.train_forward_backward(src)
         self.apply_gradients(self.all_reduce_grads())
         return out
 

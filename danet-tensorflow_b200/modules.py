@@ -212,7 +212,8 @@ class _RecurrentEncoder(Encoder):
         xc = tape[-1]['centered']
         B, T, odim = xc.shape
         main = K.torch.cuda.current_stream()
-        side = model.side_stream('grad') if model.OVERLAP_WEIGHT_GRADS else main
+        # one side stream per training slice (Model.train_forward_backward in stream groups)
+        side = model.side_stream(('grad', model._train_group)) if model.OVERLAP_WEIGHT_GRADS else main
         dx = K.gemm(d_embed2, P[self.name + '/output/W'], trans_b=True)                          # dX = dY W^T
         side.wait_stream(main)
         with K.torch.cuda.stream(side):

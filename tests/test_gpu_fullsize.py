@@ -315,6 +315,35 @@ def test_sharded_product_gradients_equal_full_batch(D):
         assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12, k
 
 
+def test_training_step_in_stream_groups_equals_one_pass(D):
+    """Model.TRAIN_GROUPS: the batch cut into slices that run forward + backward on their own streams and write their own
+    gradient buffers; the batch-weighted sum is the single-pass gradient up to summation order (loss = batch mean,
+    app/ops.py:406-431), for even and ragged splits, and one clip + Adam step leaves the same parameters"""
+    _configure(D, 1, False, BATCH_SIZE=19)
+    K = D.kernels
+    g = torch.Generator(device='cuda').manual_seed(5)
+    src = K.stft(torch.randn(19, 2, 6000, device='cuda', generator=g) * 1000.)
+    old = D.Model.TRAIN_GROUPS
+    try:
+        D.Model.TRAIN_GROUPS = 1
+        one = D.Model('one', seed=1337).build()
+        o1 = one.train_step(src)
+        for groups, gmin in ((2, 8), (4, 4)):
+            D.Model.TRAIN_GROUPS, D.Model.TRAIN_GROUP_MIN = groups, gmin
+            m = D.Model('grp%d' % groups, seed=1337).build()
+            assert m._train_group_count(19) == groups
+            o = m.train_step(src)
+            scale = float(one._flat['grad'].abs().max())
+            assert float((m._flat['grad'] - one._flat['grad']).abs().max()) < 5e-5 * scale
+            assert abs(float(o['loss']) - float(o1['loss'])) <= 1e-5 * abs(float(o1['loss']))
+            assert torch.equal(o['perm_idx'], o1['perm_idx'])
+            # Adam's first step is lr * sign(g): compare where the gradient is significant
+            sig = one._flat['grad'].abs() > 1e-3 * scale
+            assert float((m._flat['param'] - one._flat['param'])[sig].abs().max()) < 1e-6
+    finally:
+        D.Model.TRAIN_GROUPS, D.Model.TRAIN_GROUP_MIN = old, 8
+
+
 def test_streaming_front_and_back_end_cfg5(D):
     """configs[4] fed as a stream: audio arrives in ragged chunks, every frame is transformed as soon as
     its samples are in, the separated audio leaves in blocks.  Bit-identical to the batch call on the whole waveform."""

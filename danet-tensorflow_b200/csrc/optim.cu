@@ -4,7 +4,7 @@
 
 namespace danet {
 
-constexpr int kColParts = 64;
+constexpr int kColParts = 128;
 
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, long long ld, long long rows, int n, float* __restrict__ part) {
@@ -13,9 +13,15 @@ colsum_partial_kernel(const float* __restrict__ x, long long ld, long long rows,
   if (col >= n) return;
   const long long chunk = (rows + kColParts - 1) / kColParts;
   const long long lo = blockIdx.y * chunk, hi = min(rows, lo + chunk);
-  float acc = 0.f;
-  for (long long r = lo; r < hi; ++r) acc += __ldg(x + r * ld + col);
-  part[(size_t)blockIdx.y * n + col] = acc;
+  // eight loads in flight per thread (one dependent load per iteration left the pass at 1.5 TB/s)
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  long long r = lo;
+  for (; r + 8 <= hi; r += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += __ldg(x + (r + j) * ld + col);
+  }
+  for (; r < hi; ++r) a[0] += __ldg(x + r * ld + col);
+  part[(size_t)blockIdx.y * n + col] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 __global__ void __launch_bounds__(256)

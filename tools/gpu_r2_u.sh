@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python tools/ab_switch.py LSTM_LAUNCH_FIRST=0 LSTM_LAUNCH_FIRST=1 > gpurun_out/ab_launch_first.txt 2>&1; cat gpurun_out/ab_launch_first.txt
-DANET_AB=LSTM_LAUNCH_FIRST=1 DANET_LSTM_PROFILE=2 timeout 300 python tools/timeline.py > gpurun_out/timeline_launch_first.txt 2>&1; grep "#\|total" gpurun_out/timeline_launch_first.txt | cut -c1-130
+DANET_LSTM_PROFILE=1 timeout 300 python tools/timeline.py > gpurun_out/timeline_phases_insitu.txt 2>&1; grep -A2 "period" gpurun_out/timeline_phases_insitu.txt | cut -c1-400
+timeout 300 python tools/lstm_profile.py 32 2>&1 | grep -A14 "fp16 recurrent state" | head -20

@@ -69,6 +69,14 @@ if PROF:
             print('  #%02d (group %d, layer %d) entry %8.1f  exit %8.1f  = %6.1f us in the kernel, prologue %4.1f us'
                   % (i, i // 4, i % 4, ent, ext, ext - ent, ck(p[0, 11] - e)))
             continue
+        if i in (1, 6, 11):        # the phases of a step INSIDE the full schedule (cycles, steps 100-400), as tools/lstm_profile.py prints them alone
+            q = p[100:400]
+            names = ['mma:wait_begin', 'mma:h_full', 'mma:issued', 'epi:step_begin', 'epi:acc_full', 'epi:tmem_ld', 'epi:gathered',
+                     'epi:activated', 'epi:bar', 'copies_issued']
+            print('     period %.1f cycles; relative to epi:step_begin: ' % np.diff(p[100:400, 3]).mean() +
+                  ', '.join('%s %+.0f' % (n, (q[:, j] - q[:, 3]).mean()) for j, n in enumerate(names)))
+            print('     copies_issued -> next h_full %.0f, h_full -> issued %.0f, issued -> acc_full %.0f' % (
+                (p[101:401, 1] - p[100:400, 9]).mean(), (q[:, 2] - q[:, 1]).mean(), (q[:, 4] - q[:, 2]).mean()))
         print('  #%02d entry %8.1f exit %8.1f | prologue %5.1f us, step 1 done +%5.1f, step 16 +%5.1f, step 32 +%5.1f, step 64 +%5.1f, step 250 +%6.1f, loop end +%6.1f'
               % (i, ent, ext, ck(p[0, 11] - e), ck(p[1, 7] - e), ck(p[16, 7] - e), ck(p[32, 7] - e), ck(p[64, 7] - e),
                  ck(p[250, 7] - e), ck(p[0, 12] - e)))

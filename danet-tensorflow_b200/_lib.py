@@ -48,7 +48,7 @@ PROTOTYPES = {
     'danet_split_operand_time_major': (c_i, [c_f, c_ll, c_i, c_i, c_i, c_v, c_v]),
     'danet_gemm_split_pipelined': (c_i, [c_v, c_v, c_f, c_f, c_ll, c_i, c_i, c_i, c_i, c_i, c_v, C.POINTER(C.c_int), c_v]),
     'danet_lstm_seq_fwd_pipelined': (c_i, [c_f, c_ll, c_ll, C.POINTER(C.c_void_p), c_ll, c_v, c_f, c_v, c_i, c_i, c_i, c_i, c_i,
-                                           c_v, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
+                                           c_v, c_i, c_i, c_i, c_i, c_v, c_sz, c_i, c_v]),
     'danet_proj_anchor_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'danet_proj_anchor_fwd': (c_i, [c_v, c_v, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_v, c_i, c_i, c_i, c_i, c_i, c_i,
                                     c_v, c_sz, c_v]),

@@ -15,7 +15,8 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
                 const void* wh_packed,
                 float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir, int T, int B,
                 int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                const int* pre_flags = nullptr, int flag_need = 0, int flags_tm = 0, int split_tm = 0);
+                const int* pre_flags = nullptr, int flag_need = 0, int flags_tm = 0, int split_tm = 0,
+                int programmatic = 0);
 size_t lstm_tc_workspace_bytes(int n_dir, int B, int H);
 size_t lstm_tc_pack_bytes(int n_dir, int H);
 int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H, void* packed, cudaStream_t stream);
@@ -207,7 +208,8 @@ static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long lo
                              const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
                              float* cell_seq, float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T,
                              int B, int H, void* workspace, size_t workspace_bytes, int backend, void* stream,
-                             const int* pre_flags = nullptr, int flag_need = 0, int flags_tm = 0, int split_tm = 0);
+                             const int* pre_flags = nullptr, int flag_need = 0, int flags_tm = 0, int split_tm = 0,
+                             int programmatic = 0);
 
 extern "C" int danet_lstm_seq_fwd(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                                   const float* const* host_Wh, long long ldw, float* out, float* cell_seq,
@@ -232,24 +234,28 @@ extern "C" int danet_lstm_seq_fwd_packed(const float* pre, long long pre_dir_str
 // i.e. strides (4H, n_dir*4H)), B and T the same as there.  tcgen05 backends, B small enough for the 8-per-cluster kernel.
 // pre_rows_time_major: the producer was called with rows_time_major (its row tiles cover rows t*B + b).
 // out_split_time_major: emit out_split with rows t*B + b (for the NEXT layer's pipelined product) instead of b*T + t.
+// programmatic_launch: launch as a programmatic dependent of the previous kernel in `stream` (the previous layer's
+// recurrence, which triggers ~11 us before it ends): the clusters are placed on the SMs that kernel frees as it frees them
+// and run their prologue while it drains; they wait for its completion before touching global memory.  Only meaningful
+// when that kernel is the immediately preceding operation of the stream; otherwise an ordinary launch.
 extern "C" int danet_lstm_seq_fwd_pipelined(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                                             const float* const* host_Wh, long long ldw, const void* wh_packed,
                                             float* out, void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
                                             const int* pre_flags, int flag_need, int pre_rows_time_major,
-                                            int out_split_time_major, void* workspace, size_t workspace_bytes,
-                                            int backend, void* stream) {
+                                            int out_split_time_major, int programmatic_launch, void* workspace,
+                                            size_t workspace_bytes, int backend, void* stream) {
   DANET_REQUIRE(backend >= 1, DANET_E_ARG, "lstm_seq_pipelined: tcgen05 backends only (backend %d)", backend);
   DANET_REQUIRE(pre_flags && flag_need >= 1, DANET_E_ARG, "lstm_seq_pipelined: pre_flags / flag_need");
   return lstm_seq_fwd_impl(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, nullptr, nullptr, out_split,
                            out_split_kp, n_dir, T, B, H, workspace, workspace_bytes, backend, stream, pre_flags, flag_need,
-                           pre_rows_time_major, out_split_time_major);
+                           pre_rows_time_major, out_split_time_major, programmatic_launch);
 }
 
 static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                              const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
                              float* cell_seq, float* gates_seq, void* out_split, int out_split_kp, int n_dir, int T,
                              int B, int H, void* workspace, size_t workspace_bytes, int backend, void* stream,
-                             const int* pre_flags, int flag_need, int flags_tm, int split_tm) {
+                             const int* pre_flags, int flag_need, int flags_tm, int split_tm, int programmatic) {
   DANET_REQUIRE(pre && host_Wh && out && workspace, DANET_E_ARG, "lstm_seq: null pointer");
   DANET_REQUIRE(n_dir == 1 || n_dir == 2, DANET_E_SHAPE, "lstm_seq: n_dir %d", n_dir);
   for (int d = 0; d < n_dir; ++d) DANET_REQUIRE(host_Wh[d], DANET_E_ARG, "lstm_seq: null Wh[%d]", d);
@@ -276,7 +282,7 @@ static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long lo
   }
   if (backend >= 1)
     return lstm_tc_fwd(pre, pre_dir_stride, pre_row_stride, host_Wh, ldw, wh_packed, out, cell_seq, gates_seq, out_split, out_split_kp,
-                       n_dir, T, B, H, backend == 2, workspace, workspace_bytes, st, pre_flags, flag_need, flags_tm, split_tm);
+                       n_dir, T, B, H, backend == 2, workspace, workspace_bytes, st, pre_flags, flag_need, flags_tm, split_tm, programmatic);
 
   const size_t smem = lstm_smem_bytes(H);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq: H %d needs %zu B of shared memory", H, smem);

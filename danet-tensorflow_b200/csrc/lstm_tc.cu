@@ -67,6 +67,11 @@ struct LstmTcParams {
   // gen 2: emit out_split with time-major rows (t*B + b) -- the next layer's pipelined product then finishes the tiles
   // of the first / last frames of ALL utterances first, and its recurrence starts after 2 of its ~32 row tiles
   int split_tm;
+  // programmatic dependent launch (gen 2): at this step every CTA lets the NEXT kernel of the stream be scheduled
+  // (griddepcontrol.launch_dependents; -1 = only at exit).  The next layer's recurrence, launched with the programmatic
+  // attribute, is then placed on the SMs this kernel frees the moment it frees them, runs its prologue, and waits for
+  // this grid's completion (griddepcontrol.wait) before it touches global memory.
+  int pdl_trigger_step;
 };
 
 constexpr int kProfSlots = 16;
@@ -513,6 +518,10 @@ lstm_tc2_kernel(const LstmTcParams p) {
   __syncthreads();
   tc_fence_after();
   cluster_sync();
+  // launched as a programmatic dependent of the previous kernel in the stream (the previous layer's recurrence): everything
+  // above ran while that grid was draining; from here on its results (and whatever else preceded it) are complete and
+  // visible.  A no-op for a normally launched kernel.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (prof_ee) p.prof[11] = clock64();
 
   if (warp == kMmaWarp) {
@@ -610,6 +619,7 @@ lstm_tc2_kernel(const LstmTcParams p) {
         for (int d = 0; d + 1 < kPreDepth; ++d) pre_q[d][gg] = pre_q[d + 1][gg];
       }
       load_pre(s + kPreDepth, pre_q[kPreDepth - 1]);
+      if (s == p.pdl_trigger_step) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       DANET_PROF(3);
       if (s > 0) {
         mbar_wait(acc_full, (s - 1) & 1);
@@ -778,13 +788,19 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3
 }
 
 template <typename Kern>
-static int launch_cluster(Kern kern, const LstmTcParams& p, int ncta, int nb, int threads, cudaStream_t stream) {
+static int launch_cluster(Kern kern, const LstmTcParams& p, int ncta, int nb, int threads, cudaStream_t stream,
+                          bool programmatic = false) {
   const size_t smem = lstm_tc_smem_bytes(ncta);
   DANET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ncta > 8) DANET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cluster_cfg(cfg, attr, dim3(ncta, (p.B + nb - 1) / nb, p.n_dir), threads, smem, ncta, stream);
+  if (programmatic) {          // may be scheduled once the previous kernel of the stream has triggered (or finished)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   DANET_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return DANET_OK;
 }
@@ -836,7 +852,7 @@ int lstm_tc_pack_wh(const float* const* host_Wh, long long ldw, int n_dir, int H
 int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const float* const* host_Wh, long long ldw,
                 const void* wh_packed, float* out, float* cell_seq, float* gates_seq, void* out_split, int out_kp, int n_dir,
                 int T, int B, int H, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                const int* pre_flags, int flag_need, int flags_tm, int split_tm) {
+                const int* pre_flags, int flag_need, int flags_tm, int split_tm, int programmatic) {
   const int ncta = (H + kUnits - 1) / kUnits;
   DANET_REQUIRE(lstm_tc_supported(H), DANET_E_SHAPE,
                 "lstm_seq: the tcgen05 backend keeps Wh resident in one cluster's tensor memory and needs "
@@ -868,6 +884,9 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.prof = prof; p.prof_steps = prof_steps;
   p.pre_flags = pre_flags; p.flag_need = flag_need;
   p.flags_tm = flags_tm ? 1 : 0; p.split_tm = split_tm ? 1 : 0;
+  // ~11 us before the end: long enough to hide the launch of the dependent grid, short enough that its clusters, should
+  // they find free SMs elsewhere, do not sit on them for long
+  p.pdl_trigger_step = T > 16 ? T - 13 : -1;
   // The recurrence is latency-bound, so spread utterances thin: 8 per cluster (half the DSMEM bytes and
   // half the epilogue work per step) while all clusters are still co-resident, 16 per cluster otherwise.
   const int clusters8 = n_dir * ((B + 7) / 8);
@@ -919,8 +938,8 @@ int lstm_tc_fwd(const float* pre, long long pre_dir, long long pre_row, const fl
   if (pad_memset)
     DANET_CUDA(cudaMemset2DAsync(p.out_split + n_dir * H, (size_t)out_kp * 2, 0, (size_t)(out_kp - n_dir * H) * 2,
                                  (size_t)2 * B * T, stream));
-  return h_fp16 ? launch_cluster(lstm_tc2_kernel<1>, p, ncta, 8, kThreads2, stream)
-                : launch_cluster(lstm_tc2_kernel<0>, p, ncta, 8, kThreads2, stream);
+  return h_fp16 ? launch_cluster(lstm_tc2_kernel<1>, p, ncta, 8, kThreads2, stream, programmatic != 0)
+                : launch_cluster(lstm_tc2_kernel<0>, p, ncta, 8, kThreads2, stream, programmatic != 0);
 }
 
 }  // namespace danet

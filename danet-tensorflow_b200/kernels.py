@@ -334,10 +334,11 @@ def gemm_split_pipelined(a2, b2, m, n, k, T, flags, bias=None, rows_tm=False):
 
 
 def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2, wh_packed=None, pre_tm=False,
-                       split_tm=False):
+                       split_tm=False, programmatic=False):
     """lstm_seq(interleaved=True, want_split=True) on input projections that are still being produced by
     gemm_split_pipelined on another stream -> (hidden [B,T,n_dir*H], its split operand).
-    pre_tm: the producer ran with rows_tm; split_tm: emit the split operand with time-major rows (t*B + b)."""
+    pre_tm: the producer ran with rows_tm; split_tm: emit the split operand with time-major rows (t*B + b);
+    programmatic: launch as a programmatic dependent of the previous kernel on the current stream (include/danet.h)."""
     pre = _req(pre, 'pre', dim=4)
     n_dir = len(w_list)
     if tuple(pre.shape) != (T, B, n_dir, 4 * H):
@@ -356,7 +357,8 @@ def lstm_seq_pipelined(pre, w_list, in_dim, T, B, H, flags, flag_need, backend=2
         _prof_ws.append(ws)
     _lib.check(lib.danet_lstm_seq_fwd_pipelined(_p(pre), 4 * H, n_dir * 4 * H, ptrs, 4 * H, _p(wh_packed), _p(out),
                                                 _p(out_split), kp, n_dir, T, B, H, _p(flags), int(flag_need), int(pre_tm),
-                                                int(split_tm), _p(ws), ws.numel(), int(backend), _stream()),
+                                                int(split_tm), int(programmatic), _p(ws), ws.numel(), int(backend),
+                                                _stream()),
                'lstm_seq_pipelined')
     _count()
     return out, out_split

@@ -191,6 +191,9 @@ class Model(object):
     USE_CENTER_FOLD = True     # output projection with the centring folded into its epilogue
     PIPELINE_INPUT_GEMM = True # the recurrence starts on the first finished tiles of its input projections
     TIME_MAJOR_HANDOVER = True # ... whose A operand has time-major rows, so that 2 finished row tiles are enough to start
+    PROGRAMMATIC_LSTM_LAUNCH = True    # layer l+1's recurrence queued behind layer l's as a programmatic dependent (PDL)
+    _pdl_prev = None           # (priority stream, output) of the last pipelined recurrence queued
+    _flags_precleared = False
     _emit_time_major = False   # set by the encoder around a layer whose output feeds another pipelined recurrent layer
     # training forward: carry h into the recurrent product as fp16 as inference does (0.57 -> 0.47 ms per layer at cfg 2,
     # step 9.38 -> 9.14 ms).  None = the encoder decides (its TRAIN_FP16_STATE_OK): on for the purely recurrent encoders --
@@ -212,7 +215,8 @@ class Model(object):
         when a group starts (off the per-layer critical path) and the layers take them in turn; outside that (or when
         the pool is used up) a set is cleared on the spot."""
         pool = self._flag_pool
-        if pool is not None and pool[1] < self.FLAG_SETS:
+        self._flags_precleared = pool is not None and pool[1] < self.FLAG_SETS
+        if self._flags_precleared:
             pool[1] += 1
             return pool[0][pool[1] - 1]
         return K.pipeline_flags(device)
@@ -264,16 +268,26 @@ class Model(object):
                 # STAGGER_US > 0: the next group is released that long after this product STARTED instead of when it ends
                 self._stagger_event = queued if self.STAGGER_US > 0 else cur.record_event()
             K.stamp('%s gemm' % name)
-            hp_stream.wait_event(queued)
+            # Programmatic dependent launch: when this layer's input IS the previous pipelined layer's output, that layer's
+            # recurrence is the last thing queued on hp_stream, and this one needs nothing else that is not guarded by the
+            # flags (its flag set was cleared when the group started): it is queued directly behind it WITHOUT waiting for
+            # this stream, as a programmatic dependent -- its clusters take over the SMs the previous recurrence frees as it
+            # frees them (queued normally they find the product's CTAs there first: measured 23 us from one layer's exit to
+            # the next one's entry) and run their prologue while it drains.
+            pdl = bool(self.PROGRAMMATIC_LSTM_LAUNCH and self._flags_precleared and self._pdl_prev is not None
+                       and self._pdl_prev[0] is hp_stream and self._pdl_prev[1] is s_x)
+            if not pdl:
+                hp_stream.wait_event(queued)
             with torch.cuda.stream(hp_stream):
                 # only a layer that feeds another recurrent layer may emit time-major rows (the output projection cuts
                 # its row tiles per utterance): the encoder says so through _emit_time_major
                 emit_tm = bool(self.TIME_MAJOR_HANDOVER and self._emit_time_major)
                 out, out_split = K.lstm_seq_pipelined(pre, [Wf, Wb], I, T, B, hdim, flags, need, backend=backend,
-                                                      wh_packed=wh_packed, pre_tm=a_tm, split_tm=emit_tm)
+                                                      wh_packed=wh_packed, pre_tm=a_tm, split_tm=emit_tm, programmatic=pdl)
             cur.wait_stream(hp_stream)
             K.stamp('%s lstm' % name)
             self._last_split = (out, out_split, emit_tm)
+            self._pdl_prev = (hp_stream, out)
             return out
         pre = K.gemm_split(a2, w2, B * T, 8 * hdim, I, bias=bias2, out_perm_T=0 if a_tm else T).view(T, B, 2, 4 * hdim)
         if self._stagger_pending:          # see separate(): the next stream group may start now

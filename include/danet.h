@@ -157,15 +157,19 @@ int danet_zero_async(void* ptr, size_t bytes, void* stream);
  *     previous layer's recurrence called with out_split_time_major): the first and the last 128-row tile then hold the
  *     first / last 16 frames of ALL 8 utterances, the product issues its tiles alternately from the two ends of time, and
  *     both scans start after 2 of the ~32 row tiles instead of after every tile that holds some utterance's first or last
- *     frame (~9).  out_split_time_major: the recurrence emits its out_split in that row order. */
+ *     frame (~9).  out_split_time_major: the recurrence emits its out_split in that row order.
+ *   programmatic_launch: the call becomes a programmatic dependent (CUDA "PDL") of the previous kernel in `stream` -- meant
+ *     for layer l+1's recurrence queued directly behind layer l's on the same stream: its clusters take over the SMs the
+ *     previous kernel frees as it frees them and run their prologue while it drains (the previous kernel triggers ~11 us
+ *     before its end), then wait for its completion before they touch global memory. */
 int danet_gemm_split_pipelined(const void* A2, const void* B2, const float* bias, float* C, long long ldc, int M, int N,
                                int K, int T, int rows_time_major, int* tile_flags, int* flag_need, void* stream);
 int danet_lstm_seq_fwd_pipelined(const float* pre, long long pre_dir_stride, long long pre_row_stride,
                                  const float* const* host_Wh, long long ldw, const void* wh_packed, float* out,
                                  void* out_split, int out_split_kp, int n_dir, int T, int B, int H,
                                  const int* pre_flags, int flag_need, int pre_rows_time_major,
-                                 int out_split_time_major, void* workspace, size_t workspace_bytes, int backend,
-                                 void* stream);
+                                 int out_split_time_major, int programmatic_launch, void* workspace,
+                                 size_t workspace_bytes, int backend, void* stream);
 
 /* ---- K2c + K3 fused: output projection with the anchor estimator's sums in its epilogue ----
  * replaces, in ONE kernel + a per-utterance finalize, the mean-centred bias-free output layer of the encoder

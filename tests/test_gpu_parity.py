@@ -357,6 +357,66 @@ def test_lstm_seq_wide(K, n_dir, B, T, I, H):
         assert float(split[:, :, n_dir * H:].abs().max()) == 0.
 
 
+def test_pipelined_recurrences_chained_as_programmatic_dependents(K):
+    """two layers the way Model queues them: layer 1's recurrence directly behind layer 0's on the priority stream as a
+    programmatic dependent (no wait for the main stream; its product only starts when layer 0 is complete), eagerly and
+    replayed from a CUDA graph -- bit-identical to the plain sequence"""
+    B, T, H, I = 8, 200, 300, 129
+    rs = np.random.RandomState(3)
+    r = .75 / np.sqrt(H)
+    Ws0 = [cuda(rs.uniform(-r, r, (I + H, 4 * H)).astype(np.float32)) for _ in range(2)]
+    Ws1 = [cuda(rs.uniform(-r, r, (2 * H + H, 4 * H)).astype(np.float32)) for _ in range(2)]
+    bias = cuda(np.concatenate([O.lstm_bias_init(H), O.lstm_bias_init(H)]).astype(np.float32))
+    x = cuda(rs.standard_normal((B * T, I)).astype(np.float32))
+
+    def w2_of(Ws, Id):
+        w2 = K.split_operand(Ws[0][:Id], True, rows_total=8 * H, row0=0)
+        K.split_operand(Ws[1][:Id], True, out=w2, rows_total=8 * H, row0=4 * H)
+        return w2
+    w20, w21 = w2_of(Ws0, I), w2_of(Ws1, 2 * H)
+    p0, p1 = K.lstm_pack_wh(Ws0, I, H), K.lstm_pack_wh(Ws1, 2 * H, H)
+    a2 = K.split_operand_time_major(x, T)
+    # reference: plain products, plain recurrences
+    pre0 = K.gemm_split(a2, w20, B * T, 8 * H, I, bias=bias).view(T, B, 2, 4 * H)
+    h0, s0 = K.lstm_seq(pre0, Ws0, I, T, B, H, interleaved=True, want_split=True, wh_packed=p0, backend=2)
+    pre1 = K.gemm_split(s0, w21, B * T, 8 * H, 2 * H, bias=bias, out_perm_T=T).view(T, B, 2, 4 * H)
+    h1_ref = K.lstm_seq(pre1, Ws1, 2 * H, T, B, H, interleaved=True, wh_packed=p1, backend=2)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(priority=-1)
+
+    def chained():
+        cur = torch.cuda.current_stream()
+        flags = K.pipeline_flags('cuda', 2)
+        queued = cur.record_event()
+        pre, need = K.gemm_split_pipelined(a2, w20, B * T, 8 * H, I, T, flags[0], bias=bias, rows_tm=True)
+        side.wait_event(queued)
+        with torch.cuda.stream(side):
+            g0, gs0 = K.lstm_seq_pipelined(pre.view(T, B, 2, 4 * H), Ws0, I, T, B, H, flags[0], need, backend=2, wh_packed=p0,
+                                           pre_tm=True, split_tm=True)
+        cur.wait_stream(side)
+        preb, need = K.gemm_split_pipelined(gs0, w21, B * T, 8 * H, 2 * H, T, flags[1], bias=bias, rows_tm=True)
+        with torch.cuda.stream(side):           # NOT ordered after `cur`: behind layer 0's recurrence only
+            g1, _ = K.lstm_seq_pipelined(preb.view(T, B, 2, 4 * H), Ws1, 2 * H, T, B, H, flags[1], need, backend=2,
+                                         wh_packed=p1, pre_tm=True, programmatic=True)
+        cur.wait_stream(side)
+        return g0, g1
+    for _ in range(2):
+        g0, g1 = chained()
+        torch.cuda.synchronize()
+        assert torch.equal(g0, h0) and torch.equal(g1, h1_ref)
+    cap = torch.cuda.Stream()
+    cap.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(cap):
+        with torch.cuda.graph(graph, stream=cap):
+            g0, g1 = chained()
+    for _ in range(3):
+        g1.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(g0, h0) and torch.equal(g1, h1_ref)
+
+
 # ---------------------------------------------------------------- K3: attractors
 def _embed_case(rs, B, C, T, E):
     V = rs.standard_normal((B, T, 129, E)).astype(np.float32) * 3.

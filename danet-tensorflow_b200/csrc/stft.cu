@@ -179,6 +179,10 @@ constexpr int kFusedMaxC = 4;
 constexpr int kFusedMaxE = 64;
 constexpr int kFusedThreads = 512;     // phase 1: 512 threads of loads in flight; phase 2: two sources transformed at once
 
+// EQ = E / 4 as a compile-time constant (5: E = 20, 10: E = 40; 0 = any E): the embedding of a bin is then fetched by EQ
+// back-to-back 16-byte loads, and with the bin loop unrolled 4x a thread has 20-40 loads in flight instead of one dependent
+// load per FMA group -- phase 1 is latency-bound (one 140 KB block per SM).
+template <int EQ>
 __global__ void __launch_bounds__(kFusedThreads)
 mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ attractors, const float2* __restrict__ mix,
                   int C, int T, int E, int kind, float* __restrict__ wav) {
@@ -207,7 +211,7 @@ mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ att
   const long long TF = (long long)T * kBins;
   const float* Vb = embed + (size_t)b * TF * E;
   const float2* Mb = mix + (size_t)b * TF;
-#pragma unroll 2
+#pragma unroll 4
   for (int idx = tid; idx < kFramesPerBlock * kBins; idx += kFusedThreads) {
     const int slot = idx / kBins, k = idx - slot * kBins;
     const int fr = f0 + slot;
@@ -220,8 +224,7 @@ mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ att
       for (int c = 0; c < kFusedMaxC; ++c) logit[c] = 0.f;
       const float4* v4 = reinterpret_cast<const float4*>(Vb + (size_t)i * E);
       z = __ldg(Mb + i);
-      for (int e4 = 0; e4 < E / 4; ++e4) {
-        const float4 x = __ldg(v4 + e4);
+      auto dot4 = [&](const float4 x, int e4) {
 #pragma unroll
         for (int c = 0; c < kFusedMaxC; ++c)
           if (c < C) {
@@ -231,6 +234,15 @@ mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ att
             logit[c] = fmaf(x.z, a[2], logit[c]);
             logit[c] = fmaf(x.w, a[3], logit[c]);
           }
+      };
+      if (EQ > 0) {
+        float4 xs[EQ > 0 ? EQ : 1];
+#pragma unroll
+        for (int e4 = 0; e4 < EQ; ++e4) xs[e4] = __ldg(v4 + e4);
+#pragma unroll
+        for (int e4 = 0; e4 < EQ; ++e4) dot4(xs[e4], e4);
+      } else {
+        for (int e4 = 0; e4 < E / 4; ++e4) dot4(__ldg(v4 + e4), e4);
       }
       if (kind == 0) {
         float mx = logit[0];
@@ -385,10 +397,17 @@ extern "C" int danet_mask_cmul_istft_fwd(const float* embed, const float* attrac
                 "mask_cmul_istft: embed must be 16-byte, mix 8-byte aligned");
   DANET_REQUIRE(B <= 65535, DANET_E_SHAPE, "mask_cmul_istft: B %d > 65535", B);
   const size_t smem = mask_istft_smem_bytes(C);
-  DANET_CUDA(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((T + kHopsPerBlock - 1) / kHopsPerBlock, B);
-  mask_istft_kernel<<<grid, kFusedThreads, smem, as_stream(stream)>>>(embed, attractors, reinterpret_cast<const float2*>(mix_c64), C, T,
-                                                             E, kind, wav);
+  const float2* mix = reinterpret_cast<const float2*>(mix_c64);
+#define DANET_K4_LAUNCH(EQ)                                                                                         \
+  do {                                                                                                              \
+    DANET_CUDA(cudaFuncSetAttribute(mask_istft_kernel<EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mask_istft_kernel<EQ><<<grid, kFusedThreads, smem, as_stream(stream)>>>(embed, attractors, mix, C, T, E, kind, wav); \
+  } while (0)
+  if (E == 20) DANET_K4_LAUNCH(5);
+  else if (E == 40) DANET_K4_LAUNCH(10);
+  else DANET_K4_LAUNCH(0);
+#undef DANET_K4_LAUNCH
   DANET_LAUNCH_CHECK();
   return DANET_OK;
 }

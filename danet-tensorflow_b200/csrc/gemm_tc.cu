@@ -568,7 +568,8 @@ proj_anchor_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < kPPair; j += 4)
           *reinterpret_cast<float4*>(tile + lane * kPPair + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        // six anchor logits per (row, bin)
+        // six anchor logits per (row, bin).  (Measured and dropped: the same logits as [32 x 20] x [20 x 8] on mma.sync
+        // m16n8k8 3xTF32 -- 18 MMAs per bin in place of 120 FMAs per lane -- 78.9 -> 82.9 us per group of 8.)
 #pragma unroll
         for (int bs = 0; bs < 2; ++bs) {
           float lg[8];

@@ -25,6 +25,15 @@ static double window_sum() {
 
 __device__ __forceinline__ float window_at(int k) { return sinpif((float)k * (1.f / 255.f)); }
 
+// log(1 + |z|) (main.py:239-240) on the special-function unit: sqrt.approx + lg2.approx (7 instructions against ~30 for
+// sqrtf + log1pf; the kernel is bound by instruction issue, not by HBM).  Absolute error <= 2e-7 (the sum 1 + |z| rounds
+// to 6e-8; lg2.approx 2^-21.4 near 1, 3 ulp elsewhere) against values of up to ~10 and the 5e-6 gate of the STFT tests.
+__device__ __forceinline__ float log1p_abs(float re, float im) {
+  float m;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(re * re + im * im));
+  return __logf(1.f + m);
+}
+
 __global__ void __launch_bounds__(256)
 stft_kernel(const float* __restrict__ wav, int n_samples, int T, float inv_wsum,
             float2* __restrict__ spec, float* __restrict__ logmag) {
@@ -52,9 +61,13 @@ stft_kernel(const float* __restrict__ wav, int n_samples, int T, float inv_wsum,
   __syncthreads();
 
   const int g = tid >> 4, j = tid & 15;
-  const unsigned gmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+  // The transform needs its 16-thread group only, but the two groups of a warp run it in lockstep under FULL-warp
+  // barriers: with a half-warp mask per group (first build) the halves are separate convergence groups and every
+  // instruction is issued twice.  Frames beyond T are transformed too (their samples are zeros inside s_wav) and only
+  // their stores are skipped, so the whole warp always takes part.
+  const unsigned gmask = 0xFFFFFFFFu;
   const int tA = t0 + 2 * g, tB = tA + 1;
-  if (tA < T) {   // uniform across the 16-thread group
+  {
     float2 v[16];
     const float* fa = s_wav + kHop * (2 * g);
     const float* fb = fa + kHop;
@@ -74,17 +87,17 @@ stft_kernel(const float* __restrict__ wav, int n_samples, int T, float inv_wsum,
     float2* outB = outA + kBins;
     float* lmA = logmag ? logmag + ((size_t)sig * T + tA) * kBins : nullptr;
     const bool hasB = tB < T;
-    for (int k = j; k <= kFft / 2; k += 16) {
+    for (int k = j; k <= kFft / 2 && tA < T; k += 16) {
       float2 zk = buf[k];
       float2 zn = buf[(kFft - k) & (kFft - 1)];
       // A = (Zk + conj(Zn))/2 ; B = (Zk - conj(Zn))/(2i)
       float2 a = make_float2(0.5f * (zk.x + zn.x) * inv_wsum, 0.5f * (zk.y - zn.y) * inv_wsum);
       float2 b = make_float2(0.5f * (zk.y + zn.y) * inv_wsum, -0.5f * (zk.x - zn.x) * inv_wsum);
       outA[k] = a;
-      if (lmA) lmA[k] = log1pf(sqrtf(a.x * a.x + a.y * a.y));
+      if (lmA) lmA[k] = log1p_abs(a.x, a.y);
       if (hasB) {
         outB[k] = b;
-        if (lmA) lmA[kBins + k] = log1pf(sqrtf(b.x * b.x + b.y * b.y));
+        if (lmA) lmA[kBins + k] = log1p_abs(b.x, b.y);
       }
     }
   }

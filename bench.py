@@ -457,9 +457,12 @@ def main():
     other = None
     if args.extras and rank == 0:
         other = []
-        for name, b2, n2, c2, e2_, est in (('configs[3]: 3 spk, 8 s, E = 40, k-means (5 iterations)', 16, 64000, 3, 40, 'kmeans'),
-                                           ('configs[4]: one 30 s stream, anchor estimator', 1, 240000, 2, 20, 'anchor')):
-            hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD=est, INFER_ESTIMATOR_METHOD=est,
+        for name, b2, n2, c2, e2_, est, enc in (
+                ('configs[3]: 3 spk, 8 s, E = 40, k-means (5 iterations)', 16, 64000, 3, 40, 'kmeans', 'bilstm-orig'),
+                ('configs[4]: one 30 s stream, anchor estimator', 1, 240000, 2, 20, 'anchor', 'bilstm-orig'),
+                ('configs[1] shape with the lstm-orig encoder (4 x 600 unidirectional: wide tcgen05 recurrent kernel)',
+                 args.batch, N_SAMPLES, N_SPK, EMBED, 'anchor', 'lstm-orig')):
+            hp.load(dict(ENCODER_TYPE=enc, TRAIN_ESTIMATOR_METHOD=est, INFER_ESTIMATOR_METHOD=est,
                          SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=b2, EMBED_SIZE=e2_, MAX_N_SIGNAL=c2))
             hp.digest()
             m2 = D.Model('other', dev, seed=1337).build()

@@ -45,6 +45,27 @@ def test_sizes_queries_without_gpu(D):
     assert lib.danet_lstm_seq_workspace_bytes(2, 32, 300) >= 256
 
 
+def test_wide_recurrent_kernel_sizes_without_gpu(D):
+    """384 < H <= 608 (lstm-orig): the pack / workspace size queries answer for the wide tcgen05 kernel, nothing beyond"""
+    lib = D._lib.load()
+    n19 = 19 * (3 * 19 * 128 * 8 + 128) * 4                   # 19 CTAs x (57 slices x 128 rows x 8 words + 128 row scales)
+    assert lib.danet_lstm_pack_wh_bytes(1, 600) == n19
+    assert lib.danet_lstm_pack_wh_bytes(2, 608) == 2 * n19
+    assert lib.danet_lstm_pack_wh_bytes(1, 640) == 0 and lib.danet_lstm_pack_wh_bytes(1, 300) > 0
+    # exchange buffer (2 parities x 19 producers x 128 LL words of 8 bytes per group of 8 utterances) + room for an image
+    assert lib.danet_lstm_seq_workspace_bytes(1, 32, 600) >= 4 * 2 * 19 * 128 * 8 + n19
+
+
+def test_training_slices(D):
+    """Model.TRAIN_GROUPS / TRAIN_GROUP_MIN: how many stream groups a training batch is cut into"""
+    m = D.Model.__new__(D.Model)
+    assert [m._train_group_count(b) for b in (1, 8, 15, 16, 32, 256)] == [1, 1, 1, 2, 2, 2]
+    m.TRAIN_GROUPS, m.TRAIN_GROUP_MIN = 4, 4
+    assert [m._train_group_count(b) for b in (3, 8, 19, 32)] == [1, 2, 4, 4]
+    m.TRAIN_GROUPS = 0
+    assert m._train_group_count(32) == 1
+
+
 def test_hparams_defaults_and_digest(D):
     hp = D.Hyperparameter()
     assert hp.FFT_SIZE == 256 and hp.FFT_STRIDE == 64 and hp.EMBED_SIZE == 20 and hp.NUM_ANCHOR == 6

@@ -50,6 +50,7 @@ struct LstmSeqParams {
   int* counters;           // [n_dir][n_bt_total]
   int n_dir, T, B, H;
   int bt0;                 // first batch tile of this launch
+  int dir0;                // first direction of this launch
   int n_bt_total;
 };
 
@@ -61,7 +62,7 @@ lstm_seq_kernel(LstmSeqParams p) {
   float4* Ws = reinterpret_cast<float4*>(smem);            // [H][kU] float4 = 4 gates
   float* hs = smem + (size_t)H * kU * 4;                   // [kBt][ldh]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = p.dir0 + blockIdx.z;
   const int n_chunks = gridDim.x;
   const int u0 = chunk * kU, b0 = bt * kBt;
 
@@ -292,9 +293,12 @@ static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long lo
   const int n_chunks = (H + kU - 1) / kU;
   const int n_bt = (B + kBt - 1) / kBt;
   const int resident = per_sm * num_sms();
-  int bt_per_launch = resident / (n_dir * n_chunks);
+  // the directions are independent: when one batch tile of both does not fit the device (H = 600: 2 x 75 CTAs) they run
+  // in separate launches
+  const int dirs_per_launch = resident >= n_dir * n_chunks ? n_dir : 1;
+  int bt_per_launch = resident / (dirs_per_launch * n_chunks);
   DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE,
-                "lstm_seq: one batch tile needs %d resident CTAs, device holds %d", n_dir * n_chunks, resident);
+                "lstm_seq: one batch tile needs %d resident CTAs, device holds %d", n_chunks, resident);
   if (bt_per_launch > n_bt) bt_per_launch = n_bt;
   DANET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_dir * n_bt * sizeof(int), st));
   LstmSeqParams p;
@@ -309,12 +313,14 @@ static int lstm_seq_fwd_impl(const float* pre, long long pre_dir_stride, long lo
   p.counters = reinterpret_cast<int*>(workspace);
   p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
   p.n_bt_total = n_bt;
-  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
-    p.bt0 = bt0;
-    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
-    void* args[] = {&p};
-    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(n_chunks, nb, n_dir),
-                                           dim3(256), args, smem, st));
-  }
+  for (int dir0 = 0; dir0 < n_dir; dir0 += dirs_per_launch)
+    for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
+      p.bt0 = bt0;
+      p.dir0 = dir0;
+      const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
+      void* args[] = {&p};
+      DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(n_chunks, nb, dirs_per_launch),
+                                             dim3(256), args, smem, st));
+    }
   return DANET_OK;
 }

@@ -17,7 +17,9 @@ namespace danet {
 int lstm_bwd_tc(const float* d_out, float* gates, const float* cell_seq, const float* const* host_Wh, long long ldw,
                 int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
-constexpr int kKS = 4;      // split of the 4H reduction across lanes
+// kKS = split of the 4H reduction across lanes: 4 for the 16 x 16 tile (H <= 320), 16 for the 8 x 8 tile of wide layers
+// (H = 600: 256 threads per CTA instead of 64 -- with 64, pulling the 77 KB da tile of a step through L2 took ~19
+// dependent load rounds per thread: 28 us per step, 240 ms per training step of `lstm-orig`)
 
 __device__ __forceinline__ int ld_acquire_i(const int* p) {
   int v;
@@ -33,11 +35,12 @@ struct LstmBwdParams {
   long long ldw;
   int* counters;           // [n_dir][n_bt]
   int n_dir, T, B, H, bt0, n_bt_total;
+  int dir0;                // first direction of this launch (wide layers: one direction per launch)
   int ldd;                 // row stride (floats) of the shared da tile, padded against bank conflicts
 };
 
 // kBU hidden units x kBB utterances per CTA (16 x 16 for H <= 320; 8 x 8 when 4H rows no longer fit)
-template <int kBU, int kBB>
+template <int kBU, int kBB, int kKS>
 __global__ void __launch_bounds__((kBU / 2) * (kBB / 2) * kKS)
 lstm_bwd_kernel(LstmBwdParams p) {
   constexpr int NT = (kBU / 2) * (kBB / 2) * kKS;
@@ -47,7 +50,7 @@ lstm_bwd_kernel(LstmBwdParams p) {
   float* sD = sW + (size_t)kBU * G4;       // [kBB][ldd]  da_{t+1} of this batch tile
   const int ldd = p.ldd;
   const int tid = threadIdx.x;
-  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = blockIdx.z;
+  const int chunk = blockIdx.x, bt = p.bt0 + blockIdx.y, dir = p.dir0 + blockIdx.z;
   const int n_chunks = gridDim.x;
   const int u0 = chunk * kBU, b0 = bt * kBB;
 
@@ -59,7 +62,7 @@ lstm_bwd_kernel(LstmBwdParams p) {
     reinterpret_cast<float4*>(sW)[i] = w;
   }
   // thread -> 2 utterances x 2 units, one quarter of the 4H reduction; 64 tiles x 4 quarters
-  const int ks = tid & (kKS - 1), tile = tid >> 2;
+  const int ks = tid & (kKS - 1), tile = tid / kKS;
   const int tb = (tile % (kBB / 2)) * 2, tu = (tile / (kBB / 2)) * 2;   // local utterance / unit of the 2x2 tile
   const int kq = (G4 / 4 + kKS - 1) / kKS;                      // float4 per quarter (ceil)
   const int q_lo = ks * kq, q_hi = min(G4 / 4, q_lo + kq);
@@ -100,7 +103,7 @@ lstm_bwd_kernel(LstmBwdParams p) {
       }
       __syncthreads();
       {
-        constexpr int kUnroll = 4;
+        constexpr int kUnroll = 8;
         const int nq = G4 / 4, total = kBB * nq;
         const float4* src = reinterpret_cast<const float4*>(p.gates + (((size_t)dir * T + tn) * B + b0) * G4);
         const int rows_ok = min(kBB, B - b0);
@@ -140,8 +143,8 @@ lstm_bwd_kernel(LstmBwdParams p) {
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          dh[i][j] += __shfl_xor_sync(0xffffffffu, dh[i][j], 1);
-          dh[i][j] += __shfl_xor_sync(0xffffffffu, dh[i][j], 2);
+#pragma unroll
+          for (int o = 1; o < kKS; o <<= 1) dh[i][j] += __shfl_xor_sync(0xffffffffu, dh[i][j], o);
         }
     }
     if (ks == 0) {
@@ -171,7 +174,7 @@ lstm_bwd_kernel(LstmBwdParams p) {
   }
 }
 
-template <int kBU, int kBB>
+template <int kBU, int kBB, int kKS>
 static int launch_lstm_bwd(LstmBwdParams p, cudaStream_t st) {
   constexpr int NT = (kBU / 2) * (kBB / 2) * kKS;
   const int H = p.H, B = p.B, n_dir = p.n_dir;
@@ -191,25 +194,30 @@ static int launch_lstm_bwd(LstmBwdParams p, cudaStream_t st) {
   }
   const size_t smem = ((size_t)kBU * 4 * H + (size_t)kBB * p.ldd) * sizeof(float);
   DANET_REQUIRE(smem <= 227 * 1024, DANET_E_SHAPE, "lstm_seq_bwd: H %d needs %zu B of shared memory", H, smem);
-  DANET_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<kBU, kBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DANET_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<kBU, kBB, kKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel<kBU, kBB>, NT, smem));
+  DANET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel<kBU, kBB, kKS>, NT, smem));
   const int n_chunks = (H + kBU - 1) / kBU;
   const int n_bt = (B + kBB - 1) / kBB;
   const int resident = per_sm * num_sms();
-  int bt_per_launch = resident / (n_dir * n_chunks);
+  // the two directions are independent: when one batch tile of both does not fit the device (H = 600: 2 x 75 CTAs), they
+  // run in separate launches
+  const int dirs_per_launch = resident >= n_dir * n_chunks ? n_dir : 1;
+  int bt_per_launch = resident / (dirs_per_launch * n_chunks);
   DANET_REQUIRE(bt_per_launch >= 1, DANET_E_SHAPE, "lstm_seq_bwd: one batch tile needs %d resident CTAs, device holds %d",
-                n_dir * n_chunks, resident);
+                n_chunks, resident);
   if (bt_per_launch > n_bt) bt_per_launch = n_bt;
   DANET_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)n_dir * n_bt * sizeof(int), st));
   p.n_bt_total = n_bt;
-  for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
-    p.bt0 = bt0;
-    const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
-    void* args[] = {&p};
-    DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<kBU, kBB>, dim3(n_chunks, nb, n_dir), dim3(NT),
-                                           args, smem, st));
-  }
+  for (int dir0 = 0; dir0 < n_dir; dir0 += dirs_per_launch)
+    for (int bt0 = 0; bt0 < n_bt; bt0 += bt_per_launch) {
+      p.bt0 = bt0;
+      p.dir0 = dir0;
+      const int nb = (n_bt - bt0 < bt_per_launch) ? n_bt - bt0 : bt_per_launch;
+      void* args[] = {&p};
+      DANET_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<kBU, kBB, kKS>, dim3(n_chunks, nb, dirs_per_launch),
+                                             dim3(NT), args, smem, st));
+    }
   return DANET_OK;
 }
 
@@ -244,6 +252,6 @@ extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float*
   p.Wh[1] = n_dir > 1 ? host_Wh[1] : host_Wh[0];
   p.ldw = ldw;
   p.counters = reinterpret_cast<int*>(workspace);
-  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.n_bt_total = 0; p.bt0 = 0;
-  return H <= 320 ? launch_lstm_bwd<16, 16>(p, st) : launch_lstm_bwd<8, 8>(p, st);
+  p.n_dir = n_dir; p.T = T; p.B = B; p.H = H; p.n_bt_total = 0; p.bt0 = 0; p.dir0 = 0;
+  return H <= 320 ? launch_lstm_bwd<16, 16, 4>(p, st) : launch_lstm_bwd<8, 8, 16>(p, st);
 }

@@ -691,7 +691,7 @@ def test_head_backward(K, kind, est, B, C, T, E):
 
 
 # ---------------------------------------------------------------- training step (row a16)
-@pytest.mark.parametrize('B,T,I,H', [(3, 9, 40, 64), (9, 14, 129, 300), (17, 6, 600, 300)])
+@pytest.mark.parametrize('B,T,I,H', [(3, 9, 40, 64), (9, 14, 129, 300), (17, 6, 600, 300), (11, 8, 129, 600)])
 def test_lstm_layer_backward(K, B, T, I, H):
     """BPTT kernels (fp32 and tcgen05) + dW/dX products of one BiLSTM layer against torch autograd on the oracle"""
     rs = np.random.RandomState(11)
@@ -710,7 +710,7 @@ def test_lstm_layer_backward(K, B, T, I, H):
     pre = torch.empty(2, T, B, 4 * H, device='cuda')
     for d in range(2):
         K.linear(xg.view(B * T, I), Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
-    for backend in (0, 1):
+    for backend in ((0, 1) if H <= K.TC_LSTM_MAX_H else (0,)):      # wide layers (lstm-orig): the fp32 kernel's 8 x 8 x 16 tile
         p = pre.clone()
         out, cell = K.lstm_seq(p, Wg, I, T, B, H, backend=backend, keep_cell=True, keep_gates=True)
         assert rel(out, y) < 1e-4

@@ -16,6 +16,11 @@ namespace danet {
 
 int lstm_bwd_tc(const float* d_out, float* gates, const float* cell_seq, const float* const* host_Wh, long long ldw,
                 int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// wide layers (384 < H <= 608), backend 2: lstm_wide_bwd_tc.cu
+bool lstm_wide_bwd_supported(int H);
+size_t lstm_wide_bwd_workspace_bytes(int n_dir, int B, int H);
+int lstm_wide_bwd(const float* d_out, float* gates, const float* cell_seq, const float* const* host_Wh, long long ldw,
+                  int n_dir, int T, int B, int H, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // kKS = split of the 4H reduction across lanes: 4 for the 16 x 16 tile (H <= 320), 16 for the 8 x 8 tile of wide layers
 // (H = 600: 256 threads per CTA instead of 64 -- with 64, pulling the 77 KB da tile of a step through L2 took ~19
@@ -226,9 +231,13 @@ static int launch_lstm_bwd(LstmBwdParams p, cudaStream_t st) {
 using namespace danet;
 
 extern "C" size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H) {
-  (void)H;
   if (n_dir < 1 || B < 1) return 256;
-  return (((size_t)n_dir * ((B + 7) / 8) * sizeof(int)) + 255) / 256 * 256;
+  const size_t counters = (((size_t)n_dir * ((B + 7) / 8) * sizeof(int)) + 255) / 256 * 256;
+  if (H >= 4 && H % 4 == 0 && lstm_wide_bwd_supported(H)) {
+    const size_t wide = lstm_wide_bwd_workspace_bytes(n_dir, B, H);
+    return wide > counters ? wide : counters;
+  }
+  return counters;
 }
 
 extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
@@ -242,9 +251,11 @@ extern "C" int danet_lstm_seq_bwd(const float* d_out, float* gates, const float*
   DANET_REQUIRE(aligned16(gates) && aligned16(host_Wh[0]), DANET_E_ALIGN, "lstm_seq_bwd: gates / Wh must be 16-byte aligned");
   DANET_REQUIRE(workspace_bytes >= danet_lstm_seq_bwd_workspace_bytes(n_dir, B, H), DANET_E_WORKSPACE,
                 "lstm_seq_bwd: workspace too small");
-  DANET_REQUIRE(backend == 0 || backend == 1, DANET_E_ARG, "lstm_seq_bwd: backend %d", backend);
+  DANET_REQUIRE(backend >= 0 && backend <= 2, DANET_E_ARG, "lstm_seq_bwd: backend %d", backend);
   if (T == 0 || B == 0) return DANET_OK;
   cudaStream_t st = as_stream(stream);
+  if (backend == 2)
+    return lstm_wide_bwd(d_out, gates, cell_seq, host_Wh, ldw, n_dir, T, B, H, workspace, workspace_bytes, st);
   if (backend == 1) return lstm_bwd_tc(d_out, gates, cell_seq, host_Wh, ldw, n_dir, T, B, H, workspace, workspace_bytes, st);
   LstmBwdParams p;
   p.d_out = d_out; p.gates = gates; p.cell_seq = cell_seq;

@@ -748,7 +748,8 @@ def lstm_seq_bwd(d_out, gates, cell, w_list, in_dim, T, B, H, backend=None):
     """
     Backward through time [TF autodiff of main.py:125-131]: d_out [B,T,n_dir*H], gates [n_dir,T,B,4H]
     (post-activation, from lstm_seq(keep_gates=True)) are overwritten IN PLACE with the pre-activation
-    gradients da; returns `gates` (now da).
+    gradients da; returns `gates` (now da).  backend 2: the tcgen05 kernel for wide layers (TC_LSTM_MAX_H < H <=
+    TC_WIDE_MAX_H, recurrent weights as one fp16 value in the product); None: 1 up to TC_LSTM_MAX_H, else the exact fp32 one.
     """
     d_out = _req(d_out, 'd_out', dim=3)
     gates = _req(gates, 'gates', dim=4)

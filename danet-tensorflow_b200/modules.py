@@ -119,15 +119,18 @@ def _recurrent_layer_backward(model, rec, dx, bidir, need_dx, main, side):
     B, T = x.shape[0], x.shape[1]
     names = [rec['name'] + '_fwd', rec['name'] + '_bwd'] if bidir else [rec['name']]
     Ws = [P[n + '/LSTM/linear/W'] for n in names]
+    # wide layers (lstm-orig): the tcgen05 kernel with fp16 weights in the product where the forward already carried its
+    # state as fp16 (Model.train_recurrent_fp16), else the exact fp32 kernel
+    be = 2 if (K.DEFAULT_BACKEND == 1 and K.TC_LSTM_MAX_H < H <= K.TC_WIDE_MAX_H and model.train_recurrent_fp16()) else None
     if side is not main:
         # the clusters of the backward recurrence need whole SMs: queue them ahead of the side stream's tiles
         hp_stream = model._priority_twin(main)
         hp_stream.wait_stream(main)
         with K.torch.cuda.stream(hp_stream):
-            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)           # [n_dir,T,B,4H]
+            da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H, backend=be)      # [n_dir,T,B,4H]
         main.wait_stream(hp_stream)
     else:
-        da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H)
+        da = K.lstm_seq_bwd(dx, rec['gates'], rec['cell'], Ws, I, T, B, H, backend=be)
     x2 = x.reshape(B * T, I)
     out2 = rec['out'].view(B * T, -1)
     dx_prev = None

@@ -234,7 +234,10 @@ int danet_lstm_seq_fwd_packed(const float* pre, long long pre_dir_stride, long l
  * reverse, dh = d_out_t + da_{t+1} Wh^T, and overwrites `gates` ([g|i|f|o] from the forward) with
  * the pre-activation gradients da in place.  dWx / dWh / dX are danet_gemm calls on da;
  * the bias gradient is danet_colsum.  backend 0 = exact fp32 cooperative kernel, 1 = tcgen05
- * cluster kernel (Wh^T slices resident in TMEM, partial products reduce-scattered over DSMEM). */
+ * cluster kernel (Wh^T slices resident in TMEM, partial products reduce-scattered over DSMEM; H <= 384), 2 = tcgen05
+ * kernel for wide layers (384 < H <= 608, the `lstm-orig` encoder of app/modules.py:140-196): groups of ceil(H/32) CTAs,
+ * the weights as ONE fp16 value per element in TMEM (2^-12 relative), da as a scaled fp16 hi/lo pair, partial products
+ * reduce-scattered through L2 with flag-in-data words. */
 size_t danet_lstm_seq_bwd_workspace_bytes(int n_dir, int B, int H);
 int danet_lstm_seq_bwd(const float* d_out, float* gates, const float* cell_seq,
                        const float* const* host_Wh, long long ldw, int n_dir, int T, int B, int H,

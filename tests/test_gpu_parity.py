@@ -691,7 +691,8 @@ def test_head_backward(K, kind, est, B, C, T, E):
 
 
 # ---------------------------------------------------------------- training step (row a16)
-@pytest.mark.parametrize('B,T,I,H', [(3, 9, 40, 64), (9, 14, 129, 300), (17, 6, 600, 300), (11, 8, 129, 600)])
+@pytest.mark.parametrize('B,T,I,H', [(3, 9, 40, 64), (9, 14, 129, 300), (17, 6, 600, 300), (11, 8, 129, 600),
+                                     (19, 40, 64, 416)])
 def test_lstm_layer_backward(K, B, T, I, H):
     """BPTT kernels (fp32 and tcgen05) + dW/dX products of one BiLSTM layer against torch autograd on the oracle"""
     rs = np.random.RandomState(11)
@@ -710,10 +711,12 @@ def test_lstm_layer_backward(K, B, T, I, H):
     pre = torch.empty(2, T, B, 4 * H, device='cuda')
     for d in range(2):
         K.linear(xg.view(B * T, I), Wg[d], cuda(Bs[d]), time_major_T=T, backend=0, k_rows=I, out=pre[d].view(T * B, 4 * H))
-    for backend in ((0, 1) if H <= K.TC_LSTM_MAX_H else (0,)):      # wide layers (lstm-orig): the fp32 kernel's 8 x 8 x 16 tile
+    # wide layers (lstm-orig): the fp32 kernel's 8 x 8 x 16 tile, and the wide tcgen05 pair (forward fp16 state + fp8
+    # residual weights, backward fp16 weights: 2^-12 relative in the backward products)
+    for backend in ((0, 1) if H <= K.TC_LSTM_MAX_H else (0, 2)):
         p = pre.clone()
         out, cell = K.lstm_seq(p, Wg, I, T, B, H, backend=backend, keep_cell=True, keep_gates=True)
-        assert rel(out, y) < 1e-4
+        assert rel(out, y) < (1e-4 if backend < 2 else 5e-4)
         da = K.lstm_seq_bwd(cuda(dout), p, cell, Wg, I, T, B, H, backend=backend)
         dx = torch.zeros(B * T, I, device='cuda')
         for d in range(2):
@@ -723,9 +726,10 @@ def test_lstm_layer_backward(K, B, T, I, H):
                          shift_a=-1 if d == 0 else 1)
             db = K.colsum(da_d)
             K.gemm(da_d, Wg[d][:I], trans_b=True, out_perm_T=B, out=dx, accumulate=d > 0)
-            assert rel(torch.cat([dWx, dWh], 0), Wt[d].grad) < 2e-4
-            assert rel(db, Bt[d].grad) < 2e-4
-        assert rel(dx.view(B, T, I), xt.grad) < 2e-4
+            tol = 2e-4 if backend < 2 else 1e-3
+            assert rel(torch.cat([dWx, dWh], 0), Wt[d].grad) < tol
+            assert rel(db, Bt[d].grad) < tol
+        assert rel(dx.view(B, T, I), xt.grad) < (2e-4 if backend < 2 else 1e-3)
 
 
 def test_clip_adam(K):

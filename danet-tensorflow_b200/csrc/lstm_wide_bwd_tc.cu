@@ -44,15 +44,17 @@ struct LstmWideBwdParams {
   uint2* xch;              // [n_dir][groups of this launch][2 parities][dest ncta][src ncta][8 utterances][32 units], zeroed
   int n_dir, T, B, H;
   int group0;
+  long long* prof;         // nullable (DANET_LSTM_PROFILE): CTA (0,0,0), epilogue thread 0: cycles summed over the steps spent in
+                           // [0] the gather, [1] da / scale / staging, [2] waiting for the accumulators, [3] TMEM loads + publishing
 };
 
 __device__ __forceinline__ void wb_ll_store(uint2* dst, float value, uint32_t flag) {
   const unsigned long long v = ((unsigned long long)flag << 32) | __float_as_uint(value);
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint4 wb_ll_load2(const uint2* src) {
   unsigned long long a, b;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
   return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
 }
 
@@ -191,7 +193,10 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
     load_step(0, cur);
     const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
 
+    const bool prof_on = p.prof != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    long long pt[4] = {0, 0, 0, 0};
     for (int n = 0; n < T; ++n) {
+      const long long c0 = prof_on ? clock64() : 0;
       load_step(n + 1, nxt);                                 // one step ahead
       // everything that does not depend on the recurrent term first:
       //   dc = dht * kA + dc_next,  da = (dc * kI, dc * kB, dc * kC, dht * kD),  dc_next' = dc * kF
@@ -240,6 +245,7 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
           }
         if (dead) dh[0] = dh[1] = __int_as_float(0x7fc00000);          // a peer never came: visibly invalid
       }
+      const long long c1 = prof_on ? clock64() : 0;
       float da[4][UPT];
       float amax = 0.f;
 #pragma unroll
@@ -289,8 +295,10 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(b_full);
         store_da();
+        const long long c2 = prof_on ? clock64() : 0;
         // partial products of this step -> one slice per peer, published with flag n + 1
         mbar_wait(acc_full, n & 1);
+        const long long c3 = prof_on ? clock64() : 0;
         tc_fence_after();
         uint2* pub = xch + (size_t)(n & 1) * ncta * ncta * 256 + (size_t)rank * 256 + lane;      // + dest * ncta * 256 + utt * 32
         for (int t = 0; t < n_mt; ++t) {
@@ -304,10 +312,18 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
           }
         }
         tc_fence_before();
+        if (prof_on) {
+          const long long c4 = clock64();
+          pt[0] += c1 - c0; pt[1] += c2 - c1; pt[2] += c3 - c2; pt[3] += c4 - c3;
+        }
       } else {
         store_da();
       }
       cur = nxt;
+    }
+    if (prof_on) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p.prof[i] = pt[i];
     }
   }
   tc_fence_before();
@@ -340,6 +356,9 @@ int lstm_wide_bwd(const float* d_out, float* gates, const float* cell_seq, const
   p.ldw = ldw; p.n_dir = n_dir; p.T = T; p.B = B; p.H = H;
   const int n_groups = (B + kWbNB - 1) / kWbNB;
   const size_t per_group = (size_t)2 * ncta * ncta * 256;             // LL words per (direction, group)
+  p.prof = getenv("DANET_LSTM_PROFILE")                                 // the 256 spare bytes behind the exchange buffer
+               ? reinterpret_cast<long long*>(reinterpret_cast<uint2*>(workspace) + (size_t)n_dir * n_groups * per_group)
+               : nullptr;
   DANET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_dir * n_groups * per_group * sizeof(uint2), stream));
   const size_t smem = 227 * 1024;        // whole SM: the step is latency-bound (lstm_tc.cu)
   DANET_CUDA(cudaFuncSetAttribute(lstm_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -84,12 +84,12 @@ constexpr int kWProfSlots = 8;
 // flag can never be observed torn; a .v2.u32 store would formally be two 32-bit accesses).
 __device__ __forceinline__ void ll_store(uint2* dst, uint32_t payload, uint32_t flag) {
   const unsigned long long v = ((unsigned long long)flag << 32) | payload;
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
 }
 // two neighbouring LL words: (x, y) = (payload, flag) of the first, (z, w) of the second
 __device__ __forceinline__ uint4 ll_load2(const uint2* src) {
   unsigned long long a, b;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
   return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
 }
 // K-major SWIZZLE_32B: rows of 32 bytes (16 fp16 = one K16 slice), 8-row atoms of 256 contiguous bytes

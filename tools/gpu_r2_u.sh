@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SEL='test_lstm_layer_backward and 600 or test_lstm_layer_backward and 416 or test_lstm_seq_wide and 1-1-5'
-for TOOL in memcheck racecheck; do
-  timeout 1200 compute-sanitizer --tool $TOOL --print-limit 20 --log-file gpurun_out/sanitizer_wide_$TOOL.log python -m pytest tests -m gpu -q -x --timeout 1100 -k "$SEL" > gpurun_out/sanitizer_wide_$TOOL.pytest.log 2>&1
-  echo "$TOOL exit $?"; tail -2 gpurun_out/sanitizer_wide_$TOOL.pytest.log; grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/sanitizer_wide_$TOOL.log
-done
+timeout 900 python -m pytest tests -m gpu -q -x -k "backward and 600 or backward and 416 or lstm_tw" > gpurun_out/pytest_u.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_u.log
+timeout 300 python tools/lstm_wide_bwd_profile.py 32 > gpurun_out/wide_bwd_prof.txt 2>&1; cat gpurun_out/wide_bwd_prof.txt

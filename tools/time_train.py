@@ -6,7 +6,7 @@ import danet_tensorflow_b200 as D
 K = D.kernels
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 hp = D.hparams
-hp.load(dict(ENCODER_TYPE='bilstm-orig', TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
+hp.load(dict(ENCODER_TYPE=os.environ.get('ENC', 'bilstm-orig'), TRAIN_ESTIMATOR_METHOD='anchor', INFER_ESTIMATOR_METHOD='anchor',
              SEPARATOR_TYPE='dot-softmax-orig', BATCH_SIZE=B)); hp.digest()
 D.Model.TRAIN_GRAPH, D.Model.TRAIN_GROUPS = False, 1      # per-kernel events need eager one-pass steps
 model = D.Model('t', 'cuda:0').build()

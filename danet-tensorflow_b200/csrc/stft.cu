@@ -54,9 +54,22 @@ stft_kernel(const float* __restrict__ wav, int n_samples, int T, float inv_wsum,
     s_win[tid] = window_at(tid);
   }
   const long long first = (long long)kHop * t0 - kFft / 2;      // sample index of s_wav[0]
-  for (int i = tid; i < kHop * (kFramesPerBlock - 1) + kFft; i += 256) {
-    long long g = first + i;
-    s_wav[i] = (g >= 0 && g < n_samples) ? __ldg(w_in + g) : 0.f;
+  {
+    // all nine loads of a thread in flight before the first store: rolled, every iteration waited out its own global
+    // load (ncu source page: half of the kernel's stall samples sat on this store -- nine DRAM latencies in series)
+    constexpr int kN = kHop * (kFramesPerBlock - 1) + kFft, kIt = (kN + 255) / 256;
+    float v[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int i = tid + 256 * it;
+      const long long g = first + i;
+      v[it] = (i < kN && g >= 0 && g < n_samples) ? __ldg(w_in + g) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int i = tid + 256 * it;
+      if (i < kN) s_wav[i] = v[it];
+    }
   }
   __syncthreads();
 

@@ -279,17 +279,17 @@ mask_istft_kernel(const float* __restrict__ embed, const float* __restrict__ att
 #pragma unroll
         for (int c = 0; c < kFusedMaxC; ++c)
           if (c < C) {
-            m[c] = expf(logit[c] - mx);
+            m[c] = __expf(logit[c] - mx);          // ex2.approx: 2 ulp on arguments <= 0, masks move by < 1e-6
             den += m[c];
           }
-        const float inv = 1.f / den;
+        const float inv = __fdividef(1.f, den);        // den in [1, C]
 #pragma unroll
         for (int c = 0; c < kFusedMaxC; ++c)
           if (c < C) m[c] *= inv;
       } else {
 #pragma unroll
         for (int c = 0; c < kFusedMaxC; ++c)
-          if (c < C) m[c] = sigmoidf_(logit[c]);
+          if (c < C) m[c] = __fdividef(1.f, 1.f + __expf(-fmaxf(logit[c], -80.f)));
       }
     } else {
 #pragma unroll

@@ -1,11 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_final.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_final.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1])
-print('value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'train', d['train']['value'], d['train']['ms_per_step'])
-print([(k['kernel'], round(k['frac'],3)) for k in d['kernels']])
-P
+timeout 900 python -m pytest tests -m gpu -q -x -k "mask or istft or separate or fused or cfg4 or cfg2_emb or cfg5 or golden" > gpurun_out/pytest_u.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_u.log
+timeout 300 python tools/time_kernels.py > gpurun_out/time_kernels_u.txt 2>&1; grep -i "stft\|mask" gpurun_out/time_kernels_u.txt | head

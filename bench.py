@@ -514,7 +514,7 @@ def main():
                 'frac': achieved / peak_tf if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 8-utterance launch (profiles/r02_ncu_final_lstm.txt:
                 # 41.85 + 1.04 MB; the input projections stream in once, outputs stay in L2), scaled to this launch's batch
-                'traffic': 42.89e6 * B / 8.,
+                'traffic': 42.19e6 * B / 8.,       # profiles/r02_ncu_final_lstm.txt: 41.85 MB read + 0.33 MB written per launch
                 'traffic_source': 'ncu --set full, lstm_tc2_kernel<1>, 8 utterances per launch, scaled by B / 8',
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)'
                 if peaks else 'fallback',

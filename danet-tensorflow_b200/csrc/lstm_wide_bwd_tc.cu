@@ -18,7 +18,9 @@
 //     buffers by step parity: a slot of step n+2 is only rewritten after its producer has gathered every slice of step
 //     n+1, whose producers had gathered step n before they published.  Every spin is bounded (NaN instead of a hang).
 //     Measured (tools/lstm_wide_bwd_profile.py, B = 32): 7208 cycles per step -- gather 4764, da / scale / staging 772,
-//     accumulators 511, TMEM loads + publishing 1160.  Tried and dropped: watching one word per source before the full
+//     accumulators 511, TMEM loads + publishing 1160; the last source's slice arrives 2940 cycles after CTA 0 has finished
+//     publishing: the CTAs whose units sit in the last M tile get every slice at the END of the sources' publishing windows,
+//     lag by that much, and everybody waits for their partial sums.  Tried and dropped: watching one word per source before the full
 //     gather (7904), publishing the tiles in an order rotated by the source's rank (7671).
 #include <stdlib.h>
 #include <cuda_fp16.h>
@@ -48,7 +50,8 @@ struct LstmWideBwdParams {
   int n_dir, T, B, H;
   int group0;
   long long* prof;         // nullable (DANET_LSTM_PROFILE): CTA (0,0,0), epilogue thread 0: cycles summed over the steps spent in
-                           // [0] the gather, [1] da / scale / staging, [2] waiting for the accumulators, [3] TMEM loads + publishing
+                           // [0] the gather, [1] da / scale / staging, [2] waiting for the accumulators, [3] TMEM loads + publishing;
+                           // [4] from the end of its publishing to the arrival of the last source's slice
 };
 
 __device__ __forceinline__ void wb_ll_store(uint2* dst, float value, uint32_t flag) {
@@ -198,6 +201,7 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
 
     const bool prof_on = p.prof != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     long long pt[4] = {0, 0, 0, 0};
+    long long arrive_sum = 0, t_pub_end = 0;
     for (int n = 0; n < T; ++n) {
       const long long c0 = prof_on ? clock64() : 0;
       load_step(n + 1, nxt);                                 // one step ahead
@@ -221,6 +225,21 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
       if (n > 0) {
         const uint2* src = xch + (size_t)((n - 1) & 1) * ncta * ncta * 256 + (size_t)rank * ncta * 256 + bl * 32 + ub;
         const uint32_t want = (uint32_t)n;
+        if (p.prof != nullptr && warp == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+          // profile only: when has the LAST source's slice for this CTA arrived, counted from the end of this CTA's own
+          // publishing (lane s watches the last word source s stores for us; the warp reconverges behind the slowest lane):
+          // summed over the steps in prof[4]
+          if (lane < ncta) {
+            const uint2* canary = src + (size_t)lane * 256 + (7 - bl) * 32 + (31 - ub);
+            unsigned long long c = 0;
+            for (int spin = 0; spin < (1 << 16); ++spin) {
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(canary) : "memory");
+              if ((uint32_t)(c >> 32) == want) break;
+            }
+            arrive_sum += clock64() - t_pub_end;
+          }
+          __syncwarp();
+        }
         uint4 v[kWbMaxCta];
         uint32_t pend = 0;
 #pragma unroll
@@ -315,6 +334,7 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
           }
         }
         tc_fence_before();
+        if (p.prof != nullptr) t_pub_end = clock64();
         if (prof_on) {
           const long long c4 = clock64();
           pt[0] += c1 - c0; pt[1] += c2 - c1; pt[2] += c3 - c2; pt[3] += c4 - c3;
@@ -328,6 +348,7 @@ lstm_wide_bwd_kernel(const LstmWideBwdParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) p.prof[i] = pt[i];
     }
+    if (prof_on) p.prof[4] = arrive_sum;
   }
   tc_fence_before();
   __syncthreads();

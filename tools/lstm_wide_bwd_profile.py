@@ -32,7 +32,9 @@ for it in range(4):
     times.append(ev[0].elapsed_time(ev[1]) * 1e3)
 groups, ncta = (B + 7) // 8, (H + 31) // 32
 off = groups * 2 * ncta * ncta * 256 * 8
-prof = ws[off:off + 32].view(torch.int64).cpu().numpy() / float(T - 1)
+prof = ws[off:off + 40].view(torch.int64).cpu().numpy() / float(T - 1)
+print('   the last source\'s slice for CTA 0 arrives %.0f cycles after CTA 0 finished publishing (mean over the steps)' % prof[4])
+prof = prof[:4]
 print('wide BPTT kernel, B = %d, H = %d: %.1f us per launch (best of 3 warm) = %.0f ns per step' % (B, H, min(times[1:]), min(times[1:]) * 1e3 / T))
 print('   cycles per step: gather %.0f, da / scale / staging %.0f, wait for the accumulators %.0f, TMEM loads + publishing %.0f, sum %.0f'
       % (prof[0], prof[1], prof[2], prof[3], prof.sum()))
